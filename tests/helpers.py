@@ -1,0 +1,88 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+
+from oracle import configs as C
+from oracle import dyffusion_oracle as O
+from oracle.synth import SiteDropout, synth_state_dict, synth_tensor
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_json(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def golden_pt(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu")
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def model_kwargs(dataset, role):
+    kw = dict(C.MODELS[dataset]["kwargs"])
+    if role == "I":
+        kw.update(C.INTERPOLATOR_OVERRIDES[dataset])
+    return kw
+
+
+def oracle_kwargs(dataset, role):
+    """kwargs of the oracle backbone function for a dataset/role."""
+    kw = model_kwargs(dataset, role)
+    arch = C.MODELS[dataset]["arch"]
+    if arch == "unet_simple":
+        keep = ("dim", "upsample_dims", "outer_sample_mode", "dropout", "input_dropout")
+    elif arch == "unet_resnet":
+        keep = ("dim", "dim_mults", "block_dropout", "block_dropout1", "attn_dropout", "input_dropout",
+                "keep_spatial_dims", "init_padding", "init_stride")
+    else:
+        keep = ("dim", "kernel_sizes", "residual", "dropout")
+    out = {k: kw[k] for k in keep if k in kw}
+    if arch == "unet_resnet":
+        out["groups"] = kw["resnet_block_groups"]
+    return arch, out
+
+
+def forward_inputs(dataset, role, rows=2):
+    fcond = C.DIFFUSION[dataset]["forward_conditioning"]
+    tag = f"{dataset}_{role}"
+    cin, ccond, _ = C.channels(dataset, role, fcond)
+    H, W = C.DATASETS[dataset]["spatial"]
+    st = C.DATASETS[dataset]["static"]
+    x = synth_tensor(f"{tag}.x", (rows, cin, H, W))
+    cond = None
+    if ccond > 0:
+        parts = []
+        if ccond - st > 0:
+            parts.append(synth_tensor(f"{tag}.c", (rows, ccond - st, H, W)))
+        if st > 0:
+            parts.append(synth_tensor(f"{tag}.s", (rows, st, H, W), kind="mask"))
+        cond = torch.cat(parts, dim=1)
+    return x, cond
+
+
+def oracle_net(dataset, role, sd, drop=None):
+    arch, kw = oracle_kwargs(dataset, role)
+    fn = O.BACKBONES[arch]
+    return lambda x, t, c: fn(sd, x, t, c, drop=drop, **kw)
+
+
+def sampler_case_inputs(name, dataset, rows):
+    d = C.DATASETS[dataset]
+    H, W = d["spatial"]
+    ic = synth_tensor(f"{name}.ic", (rows, d["channels"], H, W))
+    static = synth_tensor(f"{name}.static", (rows, d["static"], H, W), kind="mask") if d["static"] else None
+    return ic, static
+
+
+def oracle_schedule(dk):
+    return O.Schedule(dk["timesteps"], dk["schedule"], dk["additional_interpolation_steps"],
+                      dk["additional_interpolation_steps_factor"], dk["interpolate_before_t1"], dk["sampling_schedule"])
