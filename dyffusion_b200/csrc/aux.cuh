@@ -1,0 +1,100 @@
+// Memory-bound companions of the convolution kernels: input packing/resizing, x2 upsampling + skip concat,
+// GroupNorm, the Navier-Stokes readout, time-embedding tables, weight re-packing and the sampler's elementwise steps.
+#pragma once
+#include "common.cuh"
+
+namespace dyf {
+
+// ---- fp32 NCHW sources (concat order) -> bf16 NHWC [rows, Ho, Wo, Cpad], optional bilinear resize (align_corners=False)
+struct PackParams {
+  const float* src[6];
+  int C[6];
+  int nsrc;
+  int src_rows;            // sources hold src_rows rows; output row r reads source row r % src_rows (batched calls)
+  int rows, Hi, Wi, Ho, Wo, Cpad;
+  int bilinear;            // 0 = same size copy, 1 = bilinear resize Hi x Wi -> Ho x Wo
+  __nv_bfloat16* out;
+  // "data+noise" forecaster conditioning (dyffusion.py:220-227): src[noise_src] <- w*src + (1-w)*N(0,1)
+  int noise_src;           // -1 = none
+  float noise_w;
+  uint64_t seed, stream;
+};
+int launch_pack(const PackParams& p, cudaStream_t s);
+
+// ---- x2 upsample (bilinear align_corners=False | nearest) of up to two bf16 NHWC sources into one concat buffer
+struct UpsampleParams {
+  const __nv_bfloat16* src[2];
+  int C[2];      // channels taken from each source (multiples of 8); C[1] = 0 for a single source
+  int ld[2];     // channel stride of each source
+  int rows, H, W;  // source spatial size; output is [rows, 2H, 2W, C[0]+C[1]]
+  int scale;     // 2 = upsample x2, 1 = plain concat copy
+  int bilinear;  // 1 bilinear, 0 nearest
+  __nv_bfloat16* out;
+};
+int launch_upsample(const UpsampleParams& p, cudaStream_t s);
+
+// ---- GroupNorm over bf16 NHWC (+ time scale/shift, activation, dropout, residual)
+struct GroupNormParams {
+  const __nv_bfloat16* x;   // [rows, HW, C] raw conv output (bias included)
+  __nv_bfloat16* y;         // [rows, HW, C]
+  const float* gamma;       // [C]
+  const float* beta;        // [C]
+  const float* tabA;        // [rows, C] (scale + 1) or nullptr
+  const float* tabB;        // [rows, C] shift or nullptr
+  const __nv_bfloat16* res; // optional residual [rows, HW, res_ld], added last
+  float* stats;             // [rows, G, 2] scratch (zeroed by the launcher)
+  int rows, HW, C, G, res_ld;
+  int act;
+  float eps;
+  DropCfg drop;
+};
+int launch_groupnorm(const GroupNormParams& p, cudaStream_t s);
+
+// ---- Navier-Stokes readout: ConvTranspose2d(64->Cout, k4, s2, p1) on the Hs x Ws map followed by the bilinear
+//      resize (2Hs x 2Ws) -> (Ho x Wo); only the pixels the resize samples are ever computed.  fp32 NCHW output.
+struct ReadoutParams {
+  const __nv_bfloat16* x;  // [rows, Hs, Ws, 64]
+  const float* w;          // [64, Cout, 4, 4] (ConvTranspose2d layout)
+  const float* bias;       // [Cout]
+  float* y;                // [rows, Cout, Ho, Wo]
+  int rows, Hs, Ws, Cin, Cout, Ho, Wo;
+};
+int launch_readout(const ReadoutParams& p, cudaStream_t s);
+
+// ---- time embedding -> per-layer epilogue tables
+struct TimeLayer {
+  long long w_off;    // offset (floats) of Linear(time_dim, 2C).weight in the packed buffer, -1 = no time MLP
+  long long b_off;
+  long long na_off;   // folded norm multiplier [C] (or -1 -> 1)
+  long long nb_off;   // folded norm/bias offset [C] (or -1 -> 0)
+  long long tab_off;  // offset (floats) of this layer's tables inside tabA/tabB, per row stride = C
+  int C;
+  int mode;           // 0: A = na*(scale+1), B = nb*(scale+1)+shift   1: A = scale+1, B = shift (GroupNorm layers)
+};
+struct TimeParams {
+  const float* time;      // [rows] or nullptr (no time embedding)
+  const float* packed;    // all fp32 parameters of the time path + folded norm vectors
+  long long w1_off, b1_off, w2_off, b2_off;  // time_emb_mlp.{1,3}
+  int dim, time_dim;      // sinusoidal dim, MLP width
+  const TimeLayer* layers;  // device array
+  int n_layers;
+  int rows;
+  float* tabA;            // per layer: [rows, C] at rows * tab_off
+  float* tabB;
+};
+int launch_time_tables(const TimeParams& p, cudaStream_t s);
+
+// ---- weight re-packing (finalize)
+// conv weight fp32 [O, I, KH, KW] -> bf16 [O, Kpad], k = (ky*KW+kx)*Cpad + c; optional weight standardisation
+int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
+                       int standardize, cudaStream_t s);
+// folded affine of conv-bias + eval BatchNorm: na = g*rsqrt(var+eps), nb = (bias-mean)*na + beta (bn may be null)
+int launch_fold_norm(const float* bias, const float* g, const float* beta, const float* mean, const float* var,
+                     float eps, float* na, float* nb, int C, cudaStream_t s);
+
+// ---- sampler elementwise: x_s <- x_s - a + b (a may be null => x_s <- b), optional copy of the result to `out`
+int launch_cold_update(float* x_s, const float* a, const float* b, float* out, long long n, cudaStream_t s);
+int launch_fill(float* p, float v, long long n, cudaStream_t s);
+int launch_dropout_mask(DropCfg d, long long n, uint8_t* mask, cudaStream_t s);
+
+}  // namespace dyf

@@ -1,0 +1,483 @@
+// Memory-bound kernels around the convolutions (see aux.cuh).  All activations are bf16 NHWC with 128-bit accesses
+// (8 channels per thread); network inputs/outputs are the reference's fp32 NCHW tensors.
+#include "aux.cuh"
+
+namespace dyf {
+namespace {
+
+// PyTorch area_pixel_compute_source_index for align_corners=False (bilinear resize).
+__device__ __forceinline__ void bilinear_coord(int dst, int in_size, float scale, int& i0, int& i1, float& l1) {
+  float src = scale * (dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {
+  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  float u2 = (float)b * 2.3283064365386963e-10f;
+  return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+// ------------------------------------------------------------------------------------------------ pack
+__global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
+  const long long total = (long long)p.rows * p.Ho * p.Wo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % p.Wo);
+  const int oy = (int)((idx / p.Wo) % p.Ho);
+  const int r = (int)(idx / ((long long)p.Wo * p.Ho));
+  int y0 = oy, y1 = oy, x0 = ox, x1 = ox;
+  float ly = 0.f, lx = 0.f;
+  if (p.bilinear) {
+    bilinear_coord(oy, p.Hi, (float)p.Hi / (float)p.Ho, y0, y1, ly);
+    bilinear_coord(ox, p.Wi, (float)p.Wi / (float)p.Wo, x0, x1, lx);
+  }
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const size_t plane = (size_t)p.Hi * p.Wi;
+  __nv_bfloat16* o = p.out + (size_t)idx * p.Cpad;
+  float v[8];
+  int oc = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const float* base = p.src[s] + (size_t)(r % p.src_rows) * p.C[s] * plane;
+    for (int c = 0; c < p.C[s]; ++c) {
+      const float* pl = base + (size_t)c * plane;
+      float val;
+      if (p.bilinear) {
+        val = w00 * __ldg(pl + (size_t)y0 * p.Wi + x0) + w01 * __ldg(pl + (size_t)y0 * p.Wi + x1) +
+              w10 * __ldg(pl + (size_t)y1 * p.Wi + x0) + w11 * __ldg(pl + (size_t)y1 * p.Wi + x1);
+      } else {
+        val = __ldg(pl + (size_t)oy * p.Wi + ox);
+        if (s == p.noise_src) {
+          const uint64_t e = ((uint64_t)r * p.C[s] + c) * plane + (size_t)oy * p.Wi + ox;  // per OUTPUT row
+          Philox ph(p.seed);
+          uint4 rn = ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.stream, 0x4e4f4953u);
+          val = p.noise_w * val + (1.f - p.noise_w) * gauss_from(rn.x, rn.y);
+        }
+      }
+      v[oc & 7] = val;
+      if ((++oc & 7) == 0) *reinterpret_cast<uint4*>(o + oc - 8) = pack8(v);
+    }
+  }
+  while (oc < p.Cpad) {
+    v[oc & 7] = 0.f;
+    if ((++oc & 7) == 0) *reinterpret_cast<uint4*>(o + oc - 8) = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsample x2 + concat
+__global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
+  const int Ho = p.H * p.scale, Wo = p.W * p.scale;
+  const int Ct = p.C[0] + p.C[1];
+  const int chunks = Ct >> 3;
+  const long long total = (long long)p.rows * Ho * Wo * chunks;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  const long long pix = idx / chunks;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int r = (int)(pix / ((long long)Wo * Ho));
+  const int c = ch << 3;
+  const int s = c < p.C[0] ? 0 : 1;
+  const int cs = s ? c - p.C[0] : c;
+  const __nv_bfloat16* src = p.src[s] + (size_t)r * p.H * p.W * p.ld[s] + cs;
+  uint4 outv;
+  if (p.scale == 1) {
+    outv = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)oy * p.W + ox) * p.ld[s]));
+  } else if (!p.bilinear) {
+    outv = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)(oy >> 1) * p.W + (ox >> 1)) * p.ld[s]));
+  } else {
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_coord(oy, p.H, 0.5f, y0, y1, ly);
+    bilinear_coord(ox, p.W, 0.5f, x0, x1, lx);
+    float a[8], b[8], cc[8], d[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)y0 * p.W + x0) * p.ld[s])), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)y0 * p.W + x1) * p.ld[s])), b);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)y1 * p.W + x0) * p.ld[s])), cc);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)y1 * p.W + x1) * p.ld[s])), d);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * b[j] + w10 * cc[j] + w11 * d[j];
+    outv = pack8(o);
+  }
+  *reinterpret_cast<uint4*>(p.out + (size_t)pix * Ct + c) = outv;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// pass 1: per (row, group) sum / sum of squares.  Each thread owns one fixed 8-channel chunk => one fixed group.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormParams p, int pix_per_block) {
+  __shared__ float s_acc[64][2];
+  const int r = blockIdx.y;
+  const int chunks = p.C >> 3;
+  const int cpg = p.C / p.G;  // channels per group (multiple of 8)
+  for (int i = threadIdx.x; i < p.G; i += blockDim.x) s_acc[i][0] = s_acc[i][1] = 0.f;
+  __syncthreads();
+  const int ch = threadIdx.x % chunks;
+  const int pstep = blockDim.x / chunks;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, p.HW);
+  float s1 = 0.f, s2 = 0.f;
+  const __nv_bfloat16* x = p.x + (size_t)r * p.HW * p.C + (ch << 3);
+  for (int px = p0 + threadIdx.x / chunks; px < p1; px += pstep) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)px * p.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
+  }
+  const int g = (ch << 3) / cpg;
+  atomicAdd(&s_acc[g][0], s1);
+  atomicAdd(&s_acc[g][1], s2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.G; i += blockDim.x) {
+    atomicAdd(p.stats + ((size_t)r * p.G + i) * 2 + 0, s_acc[i][0]);
+    atomicAdd(p.stats + ((size_t)r * p.G + i) * 2 + 1, s_acc[i][1]);
+  }
+}
+
+// pass 2: normalise + affine + time scale/shift + activation + dropout + residual
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormParams p) {
+  const int chunks = p.C >> 3;
+  const long long total = (long long)p.rows * p.HW * chunks;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  const long long m = idx / chunks;
+  const int r = (int)(m / p.HW);
+  const int c0 = ch << 3;
+  const int cpg = p.C / p.G;
+  const int g = c0 / cpg;
+  const float n = (float)p.HW * (float)cpg;
+  const float mean = p.stats[((size_t)r * p.G + g) * 2] / n;
+  const float var = fmaxf(p.stats[((size_t)r * p.G + g) * 2 + 1] / n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + p.eps);
+  float f[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.C + c0)), f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = (f[j] - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
+    if (p.tabA) v = v * __ldg(p.tabA + (size_t)r * p.C + c0 + j) + __ldg(p.tabB + (size_t)r * p.C + c0 + j);
+    f[j] = apply_act(v, p.act);
+  }
+  if (p.drop.thresh) {
+    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.C + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop.scale : 0.f;
+  }
+  if (p.res) {
+    float rr[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.res + (size_t)m * p.res_ld + c0)), rr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += rr[j];
+  }
+  *reinterpret_cast<uint4*>(p.y + (size_t)m * p.C + c0) = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------ NS readout
+constexpr int RO_MAXC = 4;
+__global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
+  extern __shared__ float s_w[];  // [ky][kx][co][ci]
+  const int nW = 16 * p.Cout * p.Cin;
+  for (int i = threadIdx.x; i < nW; i += blockDim.x) {
+    const int ci = i % p.Cin;
+    const int co = (i / p.Cin) % p.Cout;
+    const int kk = i / (p.Cin * p.Cout);
+    s_w[i] = p.w[((size_t)ci * p.Cout + co) * 16 + kk];
+  }
+  __syncthreads();
+  const int lanes = p.Cin >> 3;  // threads cooperating on one output pixel (8 for Cin = 64)
+  const long long total = (long long)p.rows * p.Ho * p.Wo;
+  const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lanes;
+  const int sub = threadIdx.x % lanes;
+  const bool active = pix < total;
+  const long long pp = active ? pix : 0;
+  const int ox = (int)(pp % p.Wo);
+  const int oy = (int)((pp / p.Wo) % p.Ho);
+  const int r = (int)(pp / ((long long)p.Wo * p.Ho));
+  const int H2 = 2 * p.Hs, W2 = 2 * p.Ws;
+  int Y[2], X[2];
+  float ly, lx;
+  bilinear_coord(oy, H2, (float)H2 / (float)p.Ho, Y[0], Y[1], ly);
+  bilinear_coord(ox, W2, (float)W2 / (float)p.Wo, X[0], X[1], lx);
+  const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
+  float acc[RO_MAXC] = {0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* xr = p.x + (size_t)r * p.Hs * p.Ws * p.Cin + (sub << 3);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const float wgt = wy[a] * wx[b];
+      if (wgt == 0.f) continue;
+      const int yy = Y[a], xx = X[b];
+      for (int ky = (yy + 1) & 1; ky < 4; ky += 2) {
+        const int iy = (yy + 1 - ky) >> 1;
+        if (iy < 0 || iy >= p.Hs) continue;
+        for (int kx = (xx + 1) & 1; kx < 4; kx += 2) {
+          const int ix = (xx + 1 - kx) >> 1;
+          if (ix < 0 || ix >= p.Ws) continue;
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xr + ((size_t)iy * p.Ws + ix) * p.Cin)), f);
+          const float* wk = s_w + (size_t)(ky * 4 + kx) * p.Cout * p.Cin + (sub << 3);
+          for (int co = 0; co < p.Cout; ++co) {
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d = fmaf(f[j], wk[co * p.Cin + j], d);
+            acc[co] = fmaf(wgt, d, acc[co]);
+          }
+        }
+      }
+    }
+  for (int co = 0; co < p.Cout; ++co) {
+    float v = acc[co];
+    for (int o = 1; o < lanes; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (active && sub == 0) p.y[(((size_t)r * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = v + __ldg(p.bias + co);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ time tables
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(128) time_tables_kernel(const TimeParams p) {
+  __shared__ float s_emb[256], s_h[512], s_t[512];
+  const TimeLayer L = p.layers[blockIdx.x];
+  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const bool timed = p.time != nullptr && L.w_off >= 0;
+  if (timed) {
+    const float t = p.time[r];
+    const int half = p.dim / 2;
+    const float k = -logf(10000.f) / (float)(half - 1);
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+      const float a = t * expf((float)i * k);
+      s_emb[i] = sinf(a);
+      s_emb[half + i] = cosf(a);
+    }
+    __syncthreads();
+    for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(dim, time_dim) + exact GELU
+      const float* w = p.packed + p.w1_off + (size_t)o * p.dim;
+      float s = 0.f;
+      for (int i = lane; i < p.dim; i += 32) s = fmaf(w[i], s_emb[i], s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float v = s + p.packed[p.b1_off + o];
+        s_h[o] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+      }
+    }
+    __syncthreads();
+    for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(time_dim, time_dim), then the per-block SiLU
+      const float* w = p.packed + p.w2_off + (size_t)o * p.time_dim;
+      float s = 0.f;
+      for (int i = lane; i < p.time_dim; i += 32) s = fmaf(w[i], s_h[i], s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float v = s + p.packed[p.b2_off + o];
+        s_t[o] = v / (1.f + expf(-v));
+      }
+    }
+    __syncthreads();
+  }
+  float* A = p.tabA + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
+  float* B = p.tabB + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
+  for (int c = warp; c < L.C; c += nwarp) {
+    float scale = 0.f, shift = 0.f;
+    if (timed) {
+      const float* ws = p.packed + L.w_off + (size_t)c * p.time_dim;
+      const float* wh = p.packed + L.w_off + (size_t)(L.C + c) * p.time_dim;
+      float s1 = 0.f, s2 = 0.f;
+      for (int i = lane; i < p.time_dim; i += 32) {
+        s1 = fmaf(ws[i], s_t[i], s1);
+        s2 = fmaf(wh[i], s_t[i], s2);
+      }
+      scale = warp_sum(s1) + p.packed[L.b_off + c];
+      shift = warp_sum(s2) + p.packed[L.b_off + L.C + c];
+    }
+    if (lane == 0) {
+      if (L.mode == 1) {
+        A[c] = scale + 1.f;
+        B[c] = shift;
+      } else {
+        const float na = L.na_off >= 0 ? p.packed[L.na_off + c] : 1.f;
+        const float nb = L.nb_off >= 0 ? p.packed[L.nb_off + c] : 0.f;
+        A[c] = na * (scale + 1.f);
+        B[c] = nb * (scale + 1.f) + shift;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight re-packing
+__global__ void __launch_bounds__(256) repack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                         int I, int KH, int KW, int Cpad, int Kpad, int standardize) {
+  __shared__ float s_red[2][8];
+  __shared__ float s_stat[2];
+  const int o = blockIdx.x;
+  const int n = I * KH * KW;
+  const float* wo = w + (size_t)o * n;
+  float mean = 0.f, rstd = 1.f;
+  if (standardize) {  // WeightStandardizedConv2d (unet.py:32-40): biased variance, eps = 1e-5 (fp32 inputs)
+    float s1 = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s1 += wo[i];
+    s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = s1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[0][i];
+      s_stat[0] = t / n;
+    }
+    __syncthreads();
+    mean = s_stat[0];
+    float s2 = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = wo[i] - mean; s2 += d * d; }
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) s_red[1][threadIdx.x >> 5] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[1][i];
+      s_stat[1] = rsqrtf(t / n + 1e-5f);
+    }
+    __syncthreads();
+    rstd = s_stat[1];
+  }
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    const int tap = k / Cpad, c = k - tap * Cpad;
+    float v = 0.f;
+    if (tap < KH * KW && c < I) {
+      const int ky = tap / KW, kx = tap - ky * KW;
+      v = (wo[((size_t)c * KH + ky) * KW + kx] - mean) * rstd;
+    }
+    out[(size_t)o * Kpad + k] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void fold_norm_kernel(const float* bias, const float* g, const float* beta, const float* mean,
+                                 const float* var, float eps, float* na, float* nb, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float b = bias ? bias[c] : 0.f;
+  if (g) {
+    const float a = g[c] * rsqrtf(var[c] + eps);
+    na[c] = a;
+    nb[c] = (b - mean[c]) * a + beta[c];
+  } else {
+    na[c] = 1.f;
+    nb[c] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sampler elementwise
+__global__ void cold_update_kernel(float* x_s, const float* a, const float* b, float* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = a ? (x_s[i] - a[i]) + b[i] : b[i];  // x_s - D(x0_hat, s) + D(x0_hat, s_next)  (dyffusion.py:386-388)
+  x_s[i] = v;
+  if (out) out[i] = v;
+}
+__global__ void fill_kernel(float* p, float v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 8 >= n) return;
+  const uint32_t keep = d.thresh ? drop_keep_bits8(d, (uint64_t)g * 8) : 0xFFu;
+  for (int j = 0; j < 8 && g * 8 + j < n; ++j) mask[g * 8 + j] = (keep >> j) & 1u;
+}
+
+}  // namespace
+
+int launch_pack(const PackParams& p, cudaStream_t s) {
+  if (p.Cpad % 8 != 0) { set_error("pack: Cpad must be a multiple of 8"); return -1; }
+  const long long total = (long long)p.rows * p.Ho * p.Wo;
+  pack_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  DYF_LAUNCH_OK("pack_kernel");
+  return 0;
+}
+
+int launch_upsample(const UpsampleParams& p, cudaStream_t s) {
+  if ((p.C[0] | p.C[1] | p.ld[0] | p.ld[1]) & 7) { set_error("upsample: channel counts must be multiples of 8"); return -1; }
+  const long long total = (long long)p.rows * p.H * p.scale * p.W * p.scale * ((p.C[0] + p.C[1]) >> 3);
+  upsample_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  DYF_LAUNCH_OK("upsample_kernel");
+  return 0;
+}
+
+int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
+  const int chunks = p.C >> 3;
+  if (p.C % (8 * p.G) != 0 || chunks > 256 || 256 % chunks != 0 || p.G > 64) {
+    set_error("groupnorm: unsupported channel/group configuration");
+    return -1;
+  }
+  DYF_CUDA_OK(cudaMemsetAsync(p.stats, 0, (size_t)p.rows * p.G * 2 * sizeof(float), s));
+  const int pstep = 256 / chunks;
+  int pix_per_block = pstep * 16;
+  dim3 grid(cdiv(p.HW, pix_per_block), p.rows);
+  groupnorm_stats_kernel<<<grid, 256, 0, s>>>(p, pix_per_block);
+  DYF_LAUNCH_OK("groupnorm_stats_kernel");
+  const long long total = (long long)p.rows * p.HW * chunks;
+  groupnorm_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  DYF_LAUNCH_OK("groupnorm_apply_kernel");
+  return 0;
+}
+
+int launch_readout(const ReadoutParams& p, cudaStream_t s) {
+  const int lanes = p.Cin >> 3;
+  if (p.Cout > RO_MAXC || p.Cin % 8 != 0 || lanes > 32 || (lanes & (lanes - 1)) != 0) {
+    set_error("readout: unsupported channel configuration");
+    return -1;
+  }
+  const long long total = (long long)p.rows * p.Ho * p.Wo * lanes;
+  const size_t smem = (size_t)16 * p.Cout * p.Cin * sizeof(float);
+  readout_kernel<<<cdiv(total, 256), 256, smem, s>>>(p);
+  DYF_LAUNCH_OK("readout_kernel");
+  return 0;
+}
+
+int launch_time_tables(const TimeParams& p, cudaStream_t s) {
+  if (p.dim > 256 || p.time_dim > 512) { set_error("time tables: dim too large"); return -1; }
+  if (p.n_layers == 0) return 0;
+  dim3 grid(p.n_layers, p.rows);
+  time_tables_kernel<<<grid, 128, 0, s>>>(p);
+  DYF_LAUNCH_OK("time_tables_kernel");
+  return 0;
+}
+
+int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
+                       int standardize, cudaStream_t s) {
+  repack_conv_kernel<<<O, 256, 0, s>>>(w, out, I, KH, KW, Cpad, Kpad, standardize);
+  DYF_LAUNCH_OK("repack_conv_kernel");
+  return 0;
+}
+
+int launch_fold_norm(const float* bias, const float* g, const float* beta, const float* mean, const float* var,
+                     float eps, float* na, float* nb, int C, cudaStream_t s) {
+  fold_norm_kernel<<<cdiv(C, 128), 128, 0, s>>>(bias, g, beta, mean, var, eps, na, nb, C);
+  DYF_LAUNCH_OK("fold_norm_kernel");
+  return 0;
+}
+
+int launch_cold_update(float* x_s, const float* a, const float* b, float* out, long long n, cudaStream_t s) {
+  cold_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(x_s, a, b, out, n);
+  DYF_LAUNCH_OK("cold_update_kernel");
+  return 0;
+}
+int launch_fill(float* p, float v, long long n, cudaStream_t s) {
+  fill_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, v, n);
+  DYF_LAUNCH_OK("fill_kernel");
+  return 0;
+}
+int launch_dropout_mask(DropCfg d, long long n, uint8_t* mask, cudaStream_t s) {
+  dropout_mask_kernel<<<cdiv((n + 7) / 8, 256), 256, 0, s>>>(d, n, mask);
+  DYF_LAUNCH_OK("dropout_mask_kernel");
+  return 0;
+}
+
+}  // namespace dyf

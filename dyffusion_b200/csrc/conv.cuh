@@ -1,0 +1,91 @@
+// Implicit-GEMM convolution over bf16 NHWC grids: parameters shared by the two implementations
+//   conv_mma.cu  -- mma.sync (HMMA) pipeline: any shape, used for odd/small layers
+//   conv_umma.cu -- tcgen05.mma (UMMA) + TMEM accumulators + TMA weight tiles: the heavy layers
+#pragma once
+#include "common.cuh"
+
+namespace dyf {
+
+struct ConvParams {
+  const __nv_bfloat16* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
+  const __nv_bfloat16* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
+  void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32
+  const float* tabA;         // [rows, Cout]  y = acc * A + B   (folded norm, conv bias, time scale/shift)
+  const float* tabB;         // [rows, Cout]
+  const __nv_bfloat16* res;  // optional residual added after activation+dropout, [M, res_ld]
+  int rows, Hi, Wi, Cin;
+  int Ho, Wo, Cout;
+  int KH, KW, stride, pad;
+  int K, Kpad;
+  int out_ld, out_coff, res_ld;
+  int act;
+  int out_fp32;              // 0 = bf16 NHWC, 1 = fp32 NHWC, 2 = fp32 NCHW [rows, Cout, Ho, Wo] (network heads)
+  long long M;               // rows * Ho * Wo
+  DropCfg drop;
+};
+
+// Fused epilogue for 8 consecutive output channels [c0, c0+8) of GEMM row m.  acc[8] are the fp32 accumulators.
+__device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m, int c0, const float* acc) {
+  const int HoWo = p.Ho * p.Wo;
+  const int r = (int)(m / HoWo);
+  const float* A = p.tabA + (size_t)r * p.Cout + c0;
+  const float* B = p.tabB + (size_t)r * p.Cout + c0;
+  float v[8];
+  const bool full = (c0 + 8 <= p.Cout) && ((p.Cout & 3) == 0);
+  if (full) {
+    float4 a0 = __ldg(reinterpret_cast<const float4*>(A)), a1 = __ldg(reinterpret_cast<const float4*>(A) + 1);
+    float4 b0 = __ldg(reinterpret_cast<const float4*>(B)), b1 = __ldg(reinterpret_cast<const float4*>(B) + 1);
+    float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(fmaf(acc[j], a[j], b[j]), p.act);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (c0 + j < p.Cout) ? apply_act(fmaf(acc[j], __ldg(A + j), __ldg(B + j)), p.act) : 0.f;
+  }
+  if (p.drop.thresh) {
+    uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop.scale : 0.f;
+  }
+  if (p.res) {
+    const __nv_bfloat16* rp = p.res + (size_t)m * p.res_ld + c0;
+    if (full) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    } else {
+      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (p.out_fp32 == 2) {
+    const int rem = (int)(m - (long long)r * HoWo);
+    float* o = reinterpret_cast<float*>(p.out) + ((size_t)r * p.Cout + c0) * HoWo + rem;
+    for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[(size_t)j * HoWo] = v[j];
+  } else if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.out_ld + p.out_coff + c0;
+    if (full && ((p.out_ld | p.out_coff) & 3) == 0) {
+      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + c0;
+    if (full && ((p.out_ld | p.out_coff) & 7) == 0) {
+      *reinterpret_cast<uint4*>(o) = pack8(v);
+    } else {
+      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
+// Returns 1 if the tcgen05 path took the layer, 0 if the shape is not eligible (caller falls back to the mma
+// pipeline), <0 on error.
+int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
+bool conv_umma_eligible(const ConvParams& p);
+
+}  // namespace dyf

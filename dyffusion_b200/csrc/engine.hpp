@@ -1,0 +1,117 @@
+// Host-side engine objects behind the C ABI: a backbone ("net") = parameter store + static layer plan,
+// and the DYffusion sampler that drives a forecaster and an interpolator net.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dyffusion_b200.h"
+#include "aux.cuh"
+#include "conv.cuh"
+
+namespace dyf {
+
+struct ParamSlot {
+  std::string key;
+  std::vector<int64_t> shape;
+  long long off = -1;   // offset (floats) inside Net::packed; -1 for ignored integer buffers
+  size_t numel = 0;
+  bool is_set = false;
+  bool ignored = false;  // num_batches_tracked
+};
+
+struct ConvLayer {
+  int w = -1, b = -1;                         // param slots: weight, bias
+  int bn_g = -1, bn_b = -1, bn_m = -1, bn_v = -1;  // eval BatchNorm folded into the epilogue (or -1)
+  int tw = -1, tb = -1;                       // per-block time MLP Linear(time_dim, 2*Cout)
+  int Cin = 0, Cpad = 0, Cout = 0, KH = 1, KW = 1, stride = 1, pad = 0;
+  bool standardize = false;                   // WeightStandardizedConv2d
+  int K = 0, Kpad = 0;
+  size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
+  long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
+  int table = -1;                             // index into Net::time_layers
+};
+
+struct NormLayer {  // GroupNorm applied by its own kernel
+  int g = -1, b = -1, tw = -1, tb = -1;
+  int C = 0, G = 8;
+  int table = -1;   // (scale+1, shift) table or -1
+  long long stats_off = 0;  // floats per row offset in stats scratch
+};
+
+enum OpType { OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
+constexpr int BUF_NONE = -1;
+
+struct Op {
+  OpType type;
+  int in0 = BUF_NONE, in1 = BUF_NONE, out = BUF_NONE, res = BUF_NONE;
+  int layer = -1;      // ConvLayer / NormLayer index
+  int act = ACT_NONE;
+  float drop_p = 0.f;
+  int site = 0;
+  int out_coff = 0;    // channel offset inside the output buffer (concat writes)
+  int out_mode = 0;    // 0 bf16 NHWC buffer, 2 fp32 NCHW external output
+  int c0 = 0, c1 = 0, scale = 2, bilinear = 1;  // upsample
+  int aux = 0;
+};
+
+struct Buf {
+  int H = 0, W = 0, C = 0;
+  size_t row_bytes() const { return (size_t)H * W * C * 2; }
+};
+
+struct Net {
+  dyf_net_desc d{};
+  std::vector<ParamSlot> params;
+  std::map<std::string, int> index;
+  std::vector<ConvLayer> convs;
+  std::vector<NormLayer> norms;
+  std::vector<Op> ops;
+  std::vector<Buf> bufs;
+  std::vector<TimeLayer> time_layers;
+  int t_w1 = -1, t_b1 = -1, t_w2 = -1, t_b2 = -1;
+  int ro_w = -1, ro_b = -1;  // readout params
+  int time_dim = 0;
+  long long tab_floats_per_row = 0;    // sum of C over time_layers
+  long long stats_floats_per_row = 0;
+  long long packed_floats = 0, extra_floats = 0;
+  size_t wq_elems = 0;
+  float* packed = nullptr;             // device: all fp32 params + folded vectors
+  __nv_bfloat16* wq = nullptr;         // device: packed bf16 conv weights
+  TimeLayer* d_time_layers = nullptr;  // device copy
+  bool finalized = false;
+  int Hin = 0, Win = 0;                // network grid (after the optional outer resize)
+
+  ~Net();
+  int add_param(const std::string& key, std::vector<int64_t> shape, bool ignored = false);
+  int add_buf(int H, int W, int C);
+  int build();                         // dispatch on d.arch
+  int build_unet_simple();
+  int build_convnet();
+  int build_unet_resnet();
+  int add_conv(const std::string& wkey, int Cin, int Cout, int k, int stride, int pad, bool bias = true);
+  void attach_bn(ConvLayer& c, const std::string& prefix);
+  void attach_time(int& tw, int& tb, const std::string& prefix, int C);
+  int set_param(const char* key, const void* data, const int64_t* shape, int ndim);
+  int finalize(cudaStream_t s);
+  size_t workspace_bytes(int rows) const;
+  int forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
+              const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s,
+              int noise_src = -1, float noise_w = 0.f, int src_rows = 0);
+};
+
+struct Sampler {
+  Net* F = nullptr;
+  Net* I = nullptr;
+  dyf_sampler_desc d{};
+  std::vector<double> schedule, tau, tF, refine;
+  std::vector<double> out_keys;    // reference key number of every output slot
+  std::vector<int> step_slot;      // schedule index -> output slot or -1
+  std::vector<int> refine_slot;    // refinement index -> output slot
+  int plan();
+  size_t workspace_bytes(int rows) const;
+  int run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, void* ws,
+          size_t ws_bytes, cudaStream_t s);
+};
+
+}  // namespace dyf

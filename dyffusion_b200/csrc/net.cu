@@ -1,0 +1,437 @@
+// Backbone plans: parameter bookkeeping (reference state-dict keys), weight folding/re-packing, and the per-forward
+// kernel sequence of the three hot-path networks.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace dyf {
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+Net::~Net() {
+  if (packed) cudaFree(packed);
+  if (wq) cudaFree(wq);
+  if (d_time_layers) cudaFree(d_time_layers);
+}
+
+int Net::add_param(const std::string& key, std::vector<int64_t> shape, bool ignored) {
+  ParamSlot p;
+  p.key = key;
+  p.shape = std::move(shape);
+  p.numel = 1;
+  for (auto v : p.shape) p.numel *= (size_t)v;
+  p.ignored = ignored;
+  if (!ignored) {
+    p.off = packed_floats;
+    packed_floats += (long long)round_up((int)p.numel, 4);  // keep every slot 16-byte aligned
+  }
+  index[key] = (int)params.size();
+  params.push_back(p);
+  return (int)params.size() - 1;
+}
+
+int Net::add_buf(int H, int W, int C) {
+  Buf b;
+  b.H = H; b.W = W; b.C = C;
+  bufs.push_back(b);
+  return (int)bufs.size() - 1;
+}
+
+int Net::add_conv(const std::string& prefix, int Cin, int Cout, int k, int stride, int pad, bool bias) {
+  ConvLayer c;
+  c.Cin = Cin;
+  c.Cpad = round_up(Cin, 8);
+  c.Cout = Cout;
+  c.KH = c.KW = k;
+  c.stride = stride;
+  c.pad = pad;
+  c.K = k * k * c.Cpad;
+  c.Kpad = round_up(c.K, 32);
+  c.w = add_param(prefix + ".weight", {Cout, Cin, k, k});
+  if (bias) c.b = add_param(prefix + ".bias", {Cout});
+  c.wq_off = wq_elems;
+  wq_elems += (size_t)Cout * c.Kpad;
+  c.na_off = packed_floats + extra_floats;  // resolved against the final packed size in finalize()
+  extra_floats += round_up(Cout, 4);
+  c.nb_off = packed_floats + extra_floats;
+  extra_floats += round_up(Cout, 4);
+  convs.push_back(c);
+  return (int)convs.size() - 1;
+}
+
+void Net::attach_bn(ConvLayer& c, const std::string& prefix) {
+  c.bn_g = add_param(prefix + ".weight", {c.Cout});
+  c.bn_b = add_param(prefix + ".bias", {c.Cout});
+  c.bn_m = add_param(prefix + ".running_mean", {c.Cout});
+  c.bn_v = add_param(prefix + ".running_var", {c.Cout});
+  add_param(prefix + ".num_batches_tracked", {}, true);
+}
+
+void Net::attach_time(int& tw, int& tb, const std::string& prefix, int C) {
+  if (!d.with_time_emb) return;
+  tw = add_param(prefix + ".weight", {2 * C, time_dim});
+  tb = add_param(prefix + ".bias", {2 * C});
+}
+
+// NOTE: folded vectors (na/nb) live after all parameters.  add_conv() records their offsets relative to
+// "packed_floats at that time + extra so far"; since parameters keep being appended afterwards, the offsets are
+// re-based in build() once the parameter region is complete.
+int Net::build() {
+  time_dim = d.dim * 2;
+  if (d.with_time_emb) {  // get_time_embedder (src/models/modules/misc.py:54-67)
+    t_w1 = add_param("time_emb_mlp.1.weight", {time_dim, d.dim});
+    t_b1 = add_param("time_emb_mlp.1.bias", {time_dim});
+    t_w2 = add_param("time_emb_mlp.3.weight", {time_dim, time_dim});
+    t_b2 = add_param("time_emb_mlp.3.bias", {time_dim});
+  }
+  int rc;
+  switch (d.arch) {
+    case DYF_ARCH_UNET_SIMPLE: rc = build_unet_simple(); break;
+    case DYF_ARCH_CONVNET: rc = build_convnet(); break;
+    case DYF_ARCH_UNET_RESNET: rc = build_unet_resnet(); break;
+    default: set_error("unknown arch"); return DYF_ERR_ARG;
+  }
+  if (rc) return rc;
+  // re-base folded-vector offsets behind the parameter region
+  long long cursor = packed_floats;
+  for (auto& c : convs) {
+    c.na_off = cursor; cursor += round_up(c.Cout, 4);
+    c.nb_off = cursor; cursor += round_up(c.Cout, 4);
+  }
+  extra_floats = cursor - packed_floats;
+  // time/epilogue tables: one (A, B) table per conv, one (scale+1, shift) table per timed GroupNorm
+  tab_floats_per_row = 0;
+  for (auto& c : convs) {
+    TimeLayer L{};
+    L.w_off = c.tw >= 0 ? params[c.tw].off : -1;
+    L.b_off = c.tb >= 0 ? params[c.tb].off : -1;
+    L.na_off = c.na_off;
+    L.nb_off = c.nb_off;
+    L.tab_off = tab_floats_per_row;
+    L.C = c.Cout;
+    L.mode = 0;
+    c.table = (int)time_layers.size();
+    time_layers.push_back(L);
+    tab_floats_per_row += round_up(c.Cout, 4);
+  }
+  stats_floats_per_row = 0;
+  for (auto& n : norms) {
+    n.stats_off = stats_floats_per_row;
+    stats_floats_per_row += 2 * n.G;
+    if (n.tw >= 0) {
+      TimeLayer L{};
+      L.w_off = params[n.tw].off;
+      L.b_off = params[n.tb].off;
+      L.na_off = L.nb_off = -1;
+      L.tab_off = tab_floats_per_row;
+      L.C = n.C;
+      L.mode = 1;
+      n.table = (int)time_layers.size();
+      time_layers.push_back(L);
+      tab_floats_per_row += round_up(n.C, 4);
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Navier-Stokes backbone (reference: src/models/unet_simple.py:86-197; layer table SURVEY.md A.1)
+// ---------------------------------------------------------------------------------------------------------------
+int Net::build_unet_simple() {
+  const int dim = d.dim;
+  const int cin = d.in_channels + d.cond_channels;
+  const bool resize = d.upsample_h > 0;
+  Hin = resize ? d.upsample_h : d.height;
+  Win = resize ? d.upsample_w : d.width;
+  if (Hin % 64 || Win % 64) {
+    set_error("unet_simple: the network grid (upsample_dims) must be divisible by 64 (six stride-2 stages)");
+    return DYF_ERR_UNSUPPORTED;
+  }
+  if (dim % 8) { set_error("unet_simple: dim must be a multiple of 8"); return DYF_ERR_UNSUPPORTED; }
+  int site = 1;
+  // stem: [resize ->] 1x1 conv (:113-116)
+  const int b_in = add_buf(Hin, Win, round_up(cin, 8));
+  Op pk{}; pk.type = OP_PACK; pk.out = b_in; pk.bilinear = resize ? 1 : 0;
+  ops.push_back(pk);
+  int ci = add_conv("init_conv", cin, dim, 1, 1, 0);
+  int x = add_buf(Hin, Win, dim);
+  { Op o{}; o.type = OP_CONV; o.in0 = b_in; o.out = x; o.layer = ci; o.act = ACT_NONE; o.drop_p = d.input_dropout; o.site = site++; ops.push_back(o); }
+  // encoder (:120-129): conv(k, s2) -> BN|GN -> time scale/shift -> LeakyReLU(0.2) -> Dropout
+  const int enc_out[6] = {dim * 2, dim * 2, dim * 4, dim * 8, dim * 8, dim * 8};
+  const int enc_k[6] = {4, 4, 4, 4, 2, 2}, enc_p[6] = {1, 1, 1, 1, 0, 0};
+  int skips[6];
+  int C = dim, H = Hin, W = Win;
+  for (int i = 0; i < 6; ++i) {
+    const std::string p = "input_ops." + std::to_string(i);
+    int tw = -1, tb = -1;
+    attach_time(tw, tb, p + ".time_mlp.1", enc_out[i]);
+    int li = add_conv(p + ".ops.0", C, enc_out[i], enc_k[i], 2, enc_p[i]);
+    H /= 2; W /= 2;
+    if (i < 5) {
+      attach_bn(convs[li], p + ".ops.1");
+      convs[li].tw = tw; convs[li].tb = tb;
+      int y = add_buf(H, W, enc_out[i]);
+      Op o{}; o.type = OP_CONV; o.in0 = x; o.out = y; o.layer = li; o.act = ACT_LEAKY; o.drop_p = d.dropout; o.site = site++;
+      ops.push_back(o);
+      x = y;
+    } else {  // last encoder block: GroupNorm(8) (:56, :128)
+      int raw = add_buf(H, W, enc_out[i]);
+      Op o{}; o.type = OP_CONV; o.in0 = x; o.out = raw; o.layer = li; o.act = ACT_NONE;
+      ops.push_back(o);
+      NormLayer n; n.C = enc_out[i]; n.G = 8; n.tw = tw; n.tb = tb;
+      n.g = add_param(p + ".ops.1.weight", {enc_out[i]});
+      n.b = add_param(p + ".ops.1.bias", {enc_out[i]});
+      norms.push_back(n);
+      int y = add_buf(H, W, enc_out[i]);
+      Op g{}; g.type = OP_GROUPNORM; g.in0 = raw; g.out = y; g.layer = (int)norms.size() - 1; g.act = ACT_LEAKY; g.drop_p = d.dropout; g.site = site++;
+      ops.push_back(g);
+      x = y;
+    }
+    skips[i] = x;
+    C = enc_out[i];
+  }
+  // decoder (:133-140): bilinear x2 -> conv(k-1) -> BN -> time scale/shift -> ReLU -> Dropout -> cat(skip)
+  const int dec_out[6] = {dim * 8, dim * 8, dim * 4, dim * 2, dim * 2, dim};
+  const int dec_k[6] = {1, 1, 3, 3, 3, 3}, dec_p[6] = {0, 0, 1, 1, 1, 1};
+  for (int i = 0; i < 6; ++i) {
+    const std::string p = "output_ops." + std::to_string(i);
+    const int skip = i > 0 ? skips[5 - i] : BUF_NONE;
+    const int c0 = bufs[x].C, c1 = skip >= 0 ? bufs[skip].C : 0;
+    H *= 2; W *= 2;
+    int up = add_buf(H, W, c0 + c1);
+    Op u{}; u.type = OP_UPSAMPLE; u.in0 = x; u.in1 = skip; u.out = up; u.c0 = c0; u.c1 = c1; u.scale = 2; u.bilinear = 1;
+    ops.push_back(u);
+    int tw = -1, tb = -1;
+    attach_time(tw, tb, p + ".time_mlp.1", dec_out[i]);
+    int li = add_conv(p + ".ops.1", c0 + c1, dec_out[i], dec_k[i], 1, dec_p[i]);
+    attach_bn(convs[li], p + ".ops.2");
+    convs[li].tw = tw; convs[li].tb = tb;
+    int y = add_buf(H, W, dec_out[i]);
+    Op o{}; o.type = OP_CONV; o.in0 = up; o.out = y; o.layer = li; o.act = ACT_RELU; o.drop_p = d.dropout; o.site = site++;
+    ops.push_back(o);
+    x = y;
+  }
+  // readout (:141-150) + outer resize back to the data grid (:195)
+  ro_w = add_param("readout.0.weight", {dim, d.out_channels, 4, 4});
+  ro_b = add_param("readout.0.bias", {d.out_channels});
+  Op r{}; r.type = OP_READOUT; r.in0 = x;
+  ops.push_back(r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// spring-mesh backbone (reference: src/models/simple_conv_net.py:59-131)
+// ---------------------------------------------------------------------------------------------------------------
+int Net::build_convnet() {
+  const int dim = d.dim;
+  const int cin = d.in_channels + d.cond_channels;
+  Hin = d.height; Win = d.width;
+  if (dim % 8) { set_error("SimpleConvNet: dim must be a multiple of 8"); return DYF_ERR_UNSUPPORTED; }
+  int site = 1;
+  int x = add_buf(Hin, Win, round_up(cin, 8));
+  Op pk{}; pk.type = OP_PACK; pk.out = x; pk.bilinear = 0;
+  ops.push_back(pk);
+  int C = cin;
+  for (int i = 0; i < d.n_kernels; ++i) {
+    const std::string p = "convs." + std::to_string(i);
+    const int k = d.kernel_sizes[i];
+    if (!(k & 1)) { set_error("SimpleConvNet: even kernel sizes change the grid size; unsupported"); return DYF_ERR_UNSUPPORTED; }
+    int li = add_conv(p + ".conv", C, dim, k, 1, (k - 1) / 2);
+    attach_bn(convs[li], p + ".norm");
+    attach_time(convs[li].tw, convs[li].tb, p + ".time_mlp.1", dim);
+    int y = add_buf(Hin, Win, dim);
+    Op o{}; o.type = OP_CONV; o.in0 = x; o.out = y; o.layer = li; o.act = ACT_GELU; o.drop_p = d.dropout; o.site = site++;
+    if (d.residual && C == dim) o.res = x;  // residual only when C_in == C_out (:31, :53-54)
+    ops.push_back(o);
+    x = y;
+    C = dim;
+  }
+  int hl = add_conv("head", dim, d.out_channels, 1, 1, 0);
+  Op h{}; h.type = OP_CONV; h.in0 = x; h.layer = hl; h.out_mode = 2;
+  ops.push_back(h);
+  return 0;
+}
+
+int Net::build_unet_resnet() {
+  set_error("unet.Unet (SST backbone) is not built yet in this round");
+  return DYF_ERR_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int Net::set_param(const char* key, const void* data, const int64_t* shape, int ndim) {
+  auto it = index.find(key);
+  if (it == index.end()) { set_error(std::string("unexpected state-dict key: ") + key); return DYF_ERR_ARG; }
+  ParamSlot& p = params[it->second];
+  if (p.ignored) { p.is_set = true; return 0; }
+  bool same = (int)p.shape.size() == ndim;
+  for (int i = 0; same && i < ndim; ++i) same = p.shape[i] == shape[i];
+  if (!same) { set_error(std::string("shape mismatch for ") + key); return DYF_ERR_ARG; }
+  if (!packed) {
+    DYF_CUDA_OK(cudaMalloc(&packed, (size_t)(packed_floats + extra_floats) * sizeof(float)));
+    DYF_CUDA_OK(cudaMemset(packed, 0, (size_t)(packed_floats + extra_floats) * sizeof(float)));
+  }
+  DYF_CUDA_OK(cudaMemcpy(packed + p.off, data, p.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+  p.is_set = true;
+  finalized = false;
+  return 0;
+}
+
+int Net::finalize(cudaStream_t s) {
+  for (auto& p : params)
+    if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
+  if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
+  for (auto& c : convs) {
+    int rc = launch_repack_conv(packed + params[c.w].off, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
+                                c.standardize ? 1 : 0, s);
+    if (rc) return rc;
+    const float* bias = c.b >= 0 ? packed + params[c.b].off : nullptr;
+    const bool bn = c.bn_g >= 0;
+    rc = launch_fold_norm(bias, bn ? packed + params[c.bn_g].off : nullptr, bn ? packed + params[c.bn_b].off : nullptr,
+                          bn ? packed + params[c.bn_m].off : nullptr, bn ? packed + params[c.bn_v].off : nullptr, 1e-5f,
+                          packed + c.na_off, packed + c.nb_off, c.Cout, s);
+    if (rc) return rc;
+  }
+  if (!d_time_layers && !time_layers.empty())
+    DYF_CUDA_OK(cudaMalloc(&d_time_layers, time_layers.size() * sizeof(TimeLayer)));
+  if (!time_layers.empty())
+    DYF_CUDA_OK(cudaMemcpyAsync(d_time_layers, time_layers.data(), time_layers.size() * sizeof(TimeLayer),
+                                cudaMemcpyHostToDevice, s));
+  DYF_CUDA_OK(cudaStreamSynchronize(s));
+  finalized = true;
+  return 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t Net::workspace_bytes(int rows) const {
+  size_t total = 0;
+  total += 2 * align256((size_t)tab_floats_per_row * rows * sizeof(float));
+  total += align256((size_t)stats_floats_per_row * rows * sizeof(float));
+  for (auto& b : bufs) total += align256(b.row_bytes() * rows);
+  return total + 256;
+}
+
+int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
+                 const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s, int noise_src, float noise_w,
+                 int src_rows) {
+  if (!finalized) { set_error("net not finalized (call dyf_net_finalize after loading parameters)"); return DYF_ERR_STATE; }
+  if (rows <= 0) { set_error("rows must be positive"); return DYF_ERR_ARG; }
+  if (ws_bytes < workspace_bytes(rows)) { set_error("workspace too small"); return DYF_ERR_ARG; }
+  if (d.with_time_emb && !time) { set_error("time is required (with_time_emb=True)"); return DYF_ERR_ARG; }
+  int ctot = 0;
+  for (int i = 0; i < nsrc; ++i) ctot += src_ch[i];
+  if (ctot != d.in_channels + d.cond_channels || nsrc > 6) {
+    set_error("input/condition channels do not match num_input_channels + num_conditional_channels");
+    return DYF_ERR_ARG;
+  }
+  const bool drop_on = drop && drop->mode == 1;
+  const uint64_t seed = drop ? drop->seed : 0, stream_id = drop ? drop->stream : 0;
+
+  // ---- carve the workspace
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* tabA = reinterpret_cast<float*>(base);
+  base += align256((size_t)tab_floats_per_row * rows * sizeof(float));
+  float* tabB = reinterpret_cast<float*>(base);
+  base += align256((size_t)tab_floats_per_row * rows * sizeof(float));
+  float* stats = reinterpret_cast<float*>(base);
+  base += align256((size_t)stats_floats_per_row * rows * sizeof(float));
+  std::vector<__nv_bfloat16*> bp(bufs.size());
+  for (size_t i = 0; i < bufs.size(); ++i) {
+    bp[i] = reinterpret_cast<__nv_bfloat16*>(base);
+    base += align256(bufs[i].row_bytes() * rows);
+  }
+
+  // ---- epilogue tables from the time embedding (a5)
+  {
+    TimeParams tp{};
+    tp.time = d.with_time_emb ? time : nullptr;
+    tp.packed = packed;
+    if (d.with_time_emb) {
+      tp.w1_off = params[t_w1].off; tp.b1_off = params[t_b1].off;
+      tp.w2_off = params[t_w2].off; tp.b2_off = params[t_b2].off;
+    }
+    tp.dim = d.dim; tp.time_dim = time_dim;
+    tp.layers = d_time_layers; tp.n_layers = (int)time_layers.size();
+    tp.rows = rows; tp.tabA = tabA; tp.tabB = tabB;
+    int rc = launch_time_tables(tp, s);
+    if (rc) return rc;
+  }
+
+  for (const Op& o : ops) {
+    int rc = 0;
+    switch (o.type) {
+      case OP_PACK: {
+        PackParams p{};
+        for (int i = 0; i < nsrc; ++i) { p.src[i] = srcs[i]; p.C[i] = src_ch[i]; }
+        p.nsrc = nsrc; p.src_rows = src_rows > 0 ? src_rows : rows; p.rows = rows; p.Hi = d.height; p.Wi = d.width;
+        p.Ho = bufs[o.out].H; p.Wo = bufs[o.out].W; p.Cpad = bufs[o.out].C;
+        p.bilinear = o.bilinear; p.out = bp[o.out];
+        p.noise_src = noise_src; p.noise_w = noise_w; p.seed = seed; p.stream = stream_id;
+        if (noise_src >= 0 && o.bilinear) { set_error("data+noise conditioning with an outer resize is unsupported"); return DYF_ERR_UNSUPPORTED; }
+        rc = launch_pack(p, s);
+        break;
+      }
+      case OP_CONV: {
+        const ConvLayer& c = convs[o.layer];
+        const Buf& bi = bufs[o.in0];
+        ConvParams p{};
+        p.in = bp[o.in0]; p.w = wq + c.wq_off;
+        p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C;
+        p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
+        p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
+        p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;
+        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * rows;
+        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * rows;
+        p.act = o.act; p.M = (long long)rows * p.Ho * p.Wo;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
+        if (o.out_mode == 2) { p.out = y; p.out_fp32 = 2; p.out_ld = c.Cout; }
+        else { p.out = bp[o.out]; p.out_ld = bufs[o.out].C; p.out_coff = o.out_coff; }
+        if (bi.C != c.Cpad) { set_error("internal: conv input channel mismatch"); return DYF_ERR_STATE; }
+        rc = launch_conv_umma(p, s);
+        if (rc == 0) rc = launch_conv_mma(p, s);
+        else if (rc > 0) rc = 0;
+        break;
+      }
+      case OP_UPSAMPLE: {
+        UpsampleParams p{};
+        p.src[0] = bp[o.in0]; p.C[0] = o.c0; p.ld[0] = bufs[o.in0].C;
+        p.src[1] = o.in1 >= 0 ? bp[o.in1] : bp[o.in0]; p.C[1] = o.c1; p.ld[1] = o.in1 >= 0 ? bufs[o.in1].C : 8;
+        p.rows = rows; p.H = bufs[o.in0].H; p.W = bufs[o.in0].W; p.scale = o.scale; p.bilinear = o.bilinear;
+        p.out = bp[o.out];
+        rc = launch_upsample(p, s);
+        break;
+      }
+      case OP_GROUPNORM: {
+        const NormLayer& n = norms[o.layer];
+        GroupNormParams p{};
+        p.x = bp[o.in0]; p.y = bp[o.out];
+        p.gamma = packed + params[n.g].off; p.beta = packed + params[n.b].off;
+        if (n.table >= 0) {
+          p.tabA = tabA + (size_t)time_layers[n.table].tab_off * rows;
+          p.tabB = tabB + (size_t)time_layers[n.table].tab_off * rows;
+        }
+        if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
+        p.stats = stats + (size_t)n.stats_off * rows;
+        p.rows = rows; p.HW = bufs[o.in0].H * bufs[o.in0].W; p.C = n.C; p.G = n.G; p.act = o.act; p.eps = 1e-5f;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        rc = launch_groupnorm(p, s);
+        break;
+      }
+      case OP_READOUT: {
+        ReadoutParams p{};
+        p.x = bp[o.in0]; p.w = packed + params[ro_w].off; p.bias = packed + params[ro_b].off; p.y = y;
+        p.rows = rows; p.Hs = bufs[o.in0].H; p.Ws = bufs[o.in0].W; p.Cin = bufs[o.in0].C; p.Cout = d.out_channels;
+        p.Ho = d.height; p.Wo = d.width;
+        rc = launch_readout(p, s);
+        break;
+      }
+      default: set_error("internal: unknown op"); return DYF_ERR_STATE;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace dyf

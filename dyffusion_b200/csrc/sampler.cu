@@ -1,0 +1,195 @@
+// The DYffusion sampling loop (reference: BaseDYffusion.sample_loop, src/diffusion/dyffusion.py:335-426) driven
+// natively: no Python between network calls, the two interpolator evaluations of a cold-sampling step batched into
+// one launch sequence (2R rows), the refinement calls batched as well, all on the caller's stream.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.hpp"
+
+namespace dyf {
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static bool is_int(double v) { return std::floor(v) == v; }
+
+int Sampler::plan() {
+  const int N = d.num_timesteps;
+  const int n = (int)schedule.size();
+  if (n < 1 || schedule[0] != 0.0) { set_error("sampling schedule must start at 0"); return DYF_ERR_ARG; }
+  for (int i = 1; i < n; ++i)
+    if (!(schedule[i] > schedule[i - 1])) { set_error("sampling schedule must be strictly increasing"); return DYF_ERR_ARG; }
+  // host replay of the key bookkeeping (:365-366, :395-399)
+  std::vector<double> keys;
+  std::vector<int> is_dyn(n, 0);
+  std::vector<double> step_key(n, 0.0);
+  double key = 0;
+  const double last_plus = schedule[n - 1] + 1;
+  for (int i = 0; i < n; ++i) {
+    const double s = schedule[i];
+    const bool last = s == N - 1;
+    const double s_next = i + 1 < n ? schedule[i + 1] : last_plus;
+    double t_next = INFINITY;
+    if (!last) {
+      if (i + 1 < n) t_next = tau[i + 1];
+      else { set_error("a sampling schedule that stops before the last diffusion step is not supported natively"); return DYF_ERR_UNSUPPORTED; }
+    }
+    (void)s_next;
+    is_dyn[i] = last || is_int(t_next);
+    key = s < N - 1 ? std::floor(t_next) : key + 1;
+    step_key[i] = key;
+    if (is_dyn[i]) keys.push_back(key);
+  }
+  for (double r : refine) keys.push_back(r);
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  out_keys = keys;
+  auto slot_of = [&](double k) { return (int)(std::lower_bound(out_keys.begin(), out_keys.end(), k) - out_keys.begin()); };
+  step_slot.assign(n, -1);
+  for (int i = 0; i < n; ++i)
+    if (is_dyn[i]) step_slot[i] = slot_of(step_key[i]);
+  refine_slot.clear();
+  for (double r : refine) {
+    if (!(r > 0 && r < d.interpolator_horizon)) { set_error("interpolate time must be in (0, horizon)"); return DYF_ERR_ARG; }
+    refine_slot.push_back(slot_of(r));
+  }
+  for (int i = 1; i < n; ++i)  // interpolator time range check (:484-486)
+    if (schedule[i] <= N - 1 && !(tau[i] > 0 && tau[i] < d.interpolator_horizon)) {
+      set_error("interpolate time must be in (0, horizon)");
+      return DYF_ERR_ARG;
+    }
+  return 0;
+}
+
+static int batch_cap(const dyf_sampler_desc& d, int rows) {
+  // logical interpolator calls per launch sequence; a cold-sampling step needs two (t = s_next and t = s)
+  int cap = d.max_rows_per_call > 0 ? std::max(d.max_rows_per_call, 2 * rows) : std::max(2 * rows, 256);
+  return std::max(2, cap / rows);
+}
+
+size_t Sampler::workspace_bytes(int rows) const {
+  const size_t plane = (size_t)F->d.height * F->d.width;
+  const size_t state = align256((size_t)rows * d.channels * plane * sizeof(float));
+  const int k = batch_cap(d, rows);
+  size_t total = 2 * state;                                                    // x_s, x0_hat
+  total += align256((size_t)k * rows * d.channels * plane * sizeof(float));     // interpolator outputs
+  total += align256((size_t)k * rows * sizeof(float));                          // time vector
+  total += std::max(F->workspace_bytes(rows), I->workspace_bytes(k * rows));
+  return total + 512;
+}
+
+int Sampler::run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, void* ws,
+                 size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < workspace_bytes(rows)) { set_error("sampler workspace too small"); return DYF_ERR_ARG; }
+  if ((d.static_channels > 0) != (stat != nullptr)) { set_error("static_condition does not match static_channels"); return DYF_ERR_ARG; }
+  const int N = d.num_timesteps, n = (int)schedule.size(), C = d.channels;
+  const size_t plane = (size_t)F->d.height * F->d.width;
+  const size_t state_n = (size_t)rows * C * plane;
+  const int kmax = batch_cap(d, rows);
+
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  float* x_s = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
+  float* x0_hat = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
+  float* ybuf = reinterpret_cast<float*>(base); base += align256((size_t)kmax * state_n * sizeof(float));
+  float* tbuf = reinterpret_cast<float*>(base); base += align256((size_t)kmax * rows * sizeof(float));
+  void* net_ws = base;
+  const size_t net_ws_bytes = ws_bytes - (size_t)(base - reinterpret_cast<uint8_t*>(ws));
+
+  // x_s = initial_condition[:, -C:]  (:348)
+  DYF_CUDA_OK(cudaMemcpy2DAsync(x_s, (size_t)C * plane * sizeof(float),
+                                ic + (size_t)(d.window_channels - C) * plane,
+                                (size_t)d.window_channels * plane * sizeof(float), (size_t)C * plane * sizeof(float),
+                                rows, cudaMemcpyDeviceToDevice, s));
+  uint64_t call = 0;
+  const bool f_cond_first = F->d.arch == DYF_ARCH_UNET_RESNET;  // unet.py:269 concatenates the condition first
+  const bool i_cond_first = I->d.arch == DYF_ARCH_UNET_RESNET;
+
+  auto run_F = [&](int idx) -> int {  // predict_x_last (:205-239)
+    const float* srcs[4];
+    int ch[4];
+    int ns = 0, noise_src = -1;
+    float noise_w = 0.f;
+    auto push_cond = [&]() {
+      if (d.forward_conditioning != 0) {
+        if (d.forward_conditioning == 2) { noise_src = ns; noise_w = (float)(schedule[idx] / (double)(N - 1)); }
+        srcs[ns] = ic; ch[ns++] = d.window_channels;
+      }
+      if (stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
+    };
+    if (f_cond_first) push_cond();
+    srcs[ns] = x_s; ch[ns++] = C;
+    if (!f_cond_first) push_cond();
+    int rc = launch_fill(tbuf, (float)tF[idx], rows, s);
+    if (rc) return rc;
+    dyf_dropout dr{0, seed, call++};
+    return F->forward(rows, srcs, ch, ns, tbuf, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows);
+  };
+  // k logical interpolator calls at times t[0..k) sharing the inputs (ic, x0_hat); outputs land in ybuf[j]
+  auto run_I = [&](const double* t, int k) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
+    const float* srcs[4];
+    int ch[4];
+    int ns = 0;
+    if (i_cond_first && stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
+    srcs[ns] = ic; ch[ns++] = d.window_channels;
+    srcs[ns] = x0_hat; ch[ns++] = C;
+    if (!i_cond_first && stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
+    for (int j = 0; j < k; ++j) {
+      int rc = launch_fill(tbuf + (size_t)j * rows, (float)t[j], rows, s);
+      if (rc) return rc;
+    }
+    dyf_dropout dr{d.enable_interpolator_dropout ? 1 : 0, seed, call};
+    call += k;
+    return I->forward(k * rows, srcs, ch, ns, tbuf, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows);
+  };
+
+  for (int i = 0; i < n; ++i) {
+    const double sstep = schedule[i];
+    const bool last = sstep == N - 1;
+    int rc = run_F(i);
+    if (rc) return rc;
+    const bool has_next = i + 1 < n && schedule[i + 1] <= N - 1;
+    float* out = step_slot[i] >= 0 ? preds + (size_t)step_slot[i] * state_n : nullptr;
+    if (d.sampling_type == 0) {  // cold (:381-388)
+      if (last && !d.use_cold_sampling_for_last_step) {
+        rc = launch_cold_update(x_s, nullptr, x0_hat, out, (long long)state_n, s);
+      } else {
+        double t[2];
+        int k = 0;
+        if (has_next) t[k++] = tau[i + 1];
+        const bool need_cur = sstep > 0;
+        if (need_cur) t[k++] = tau[i];
+        const float* x_next = x0_hat;
+        const float* x_cur = nullptr;
+        if (k > 0) {
+          rc = run_I(t, k);
+          if (rc) return rc;
+          if (has_next) { x_next = ybuf; if (need_cur) x_cur = ybuf + state_n; }
+          else if (need_cur) x_cur = ybuf;
+        }
+        if (need_cur) rc = launch_cold_update(x_s, x_cur, x_next, out, (long long)state_n, s);
+        else rc = launch_cold_update(x_s, nullptr, x_next, out, (long long)state_n, s);  // s == 0: x_s <- x_next
+      }
+    } else {  // naive (:390-391)
+      const float* x_next = x0_hat;
+      if (has_next) {
+        double t = tau[i + 1];
+        rc = run_I(&t, 1);
+        if (rc) return rc;
+        x_next = ybuf;
+      }
+      rc = launch_cold_update(x_s, nullptr, x_next, out, (long long)state_n, s);
+    }
+    if (rc) return rc;
+  }
+  // refinement of the intermediate predictions with the final x0_hat (:408-422)
+  for (size_t j0 = 0; j0 < refine.size(); j0 += kmax) {
+    const int k = (int)std::min<size_t>(kmax, refine.size() - j0);
+    int rc = run_I(&refine[j0], k);
+    if (rc) return rc;
+    for (int j = 0; j < k; ++j)
+      DYF_CUDA_OK(cudaMemcpyAsync(preds + (size_t)refine_slot[j0 + j] * state_n, ybuf + (size_t)j * state_n,
+                                  state_n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (x0_out) DYF_CUDA_OK(cudaMemcpyAsync(x0_out, x0_hat, state_n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+}  // namespace dyf

@@ -1,0 +1,173 @@
+/* dyffusion_b200 -- C ABI of the B200-native DYffusion sampling engine.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no FFI of its own for this
+ * path: its "plug-in" interface is two Hydra `_target_` classes (model + diffusion) whose arithmetic runs in
+ * PyTorch/ATen.  The Python drop-in classes in `dyffusion_b200/` keep that surface (same constructor kwargs,
+ * state-dict keys, `forward/predict_forward/sample/sample_loop`) and forward the arithmetic to the entry points
+ * below through ctypes.  Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions: plain C, no C++ types or exceptions across the boundary.  Every function returns 0 on success and
+ * a negative code on failure; `dyf_last_error()` returns a thread-local message (the Python side raises it as
+ * RuntimeError -- the reference signals errors with Python exceptions, e.g. src/diffusion/dyffusion.py:42,47,68).
+ * All data pointers are DEVICE pointers owned by the caller unless stated otherwise; tensors are fp32, NCHW,
+ * contiguous, exactly as the reference passes them.  The engine owns only its handles (re-packed weights, layer
+ * plans).  Workspace is caller-allocated and sized by a query.  All work is enqueued on the caller's stream
+ * (`void*` = cudaStream_t); no host synchronisation, no internal threads.  Handles are not thread-safe.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with DYF_ERR_CUDA.
+ */
+#ifndef DYFFUSION_B200_H
+#define DYFFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
+
+#define DYF_ABI_VERSION 1
+
+enum { DYF_OK = 0, DYF_ERR_ARG = -1, DYF_ERR_CUDA = -2, DYF_ERR_STATE = -3, DYF_ERR_UNSUPPORTED = -4 };
+
+/* Backbones on the hot path. */
+enum {
+  DYF_ARCH_UNET_SIMPLE = 0, /* src/models/unet_simple.py:86-197   (Navier-Stokes)  */
+  DYF_ARCH_UNET_RESNET = 1, /* src/models/unet.py:114-315          (SST)            */
+  DYF_ARCH_CONVNET = 2      /* src/models/simple_conv_net.py:59-131 (spring-mesh)   */
+};
+
+/* Constructor arguments of the three reference backbones that change the arithmetic. */
+typedef struct dyf_net_desc {
+  int32_t arch;
+  int32_t dim;             /* `dim` */
+  int32_t in_channels;     /* num_input_channels  (src/models/_base_model.py:44-46)            */
+  int32_t cond_channels;   /* num_conditional_channels                                          */
+  int32_t out_channels;    /* num_output_channels                                               */
+  int32_t height, width;   /* spatial_shape                                                     */
+  int32_t with_time_emb;   /* `with_time_emb` */
+  /* unet_simple.UNet */
+  int32_t upsample_h, upsample_w; /* `upsample_dims` (0,0 = None)   unet_simple.py:91,98-101     */
+  float dropout;           /* `dropout` (unet_simple / SimpleConvNet)                            */
+  float input_dropout;     /* `input_dropout` (unet_simple / Unet)                               */
+  /* unet.Unet */
+  int32_t n_mults;
+  int32_t dim_mults[8];    /* `dim_mults` */
+  int32_t groups;          /* `resnet_block_groups` */
+  float block_dropout;     /* dropout of block2 (unet.py:151) */
+  float block_dropout1;    /* dropout of block1 (unet.py:150) */
+  float attn_dropout;      /* unet.py:187,209 */
+  int32_t keep_spatial_dims;
+  int32_t init_kernel, init_padding, init_stride;
+  /* SimpleConvNet */
+  int32_t n_kernels;
+  int32_t kernel_sizes[8]; /* `kernel_sizes` */
+  int32_t residual;        /* `residual` */
+} dyf_net_desc;
+
+typedef struct dyf_net dyf_net;
+typedef struct dyf_sampler dyf_sampler;
+
+/* Dropout control of one forward.  mode 0 = off (the reference's eval mode), 1 = on with the engine's
+ * counter-based Philox stream keyed by (seed, stream) (the reference's "inference dropout",
+ * src/utilities/utils.py:560-574 + src/models/_base_model.py:148-161).  `stream` must differ between calls that
+ * must draw independent masks. */
+typedef struct dyf_dropout {
+  int32_t mode;
+  uint64_t seed;
+  uint64_t stream;
+} dyf_dropout;
+
+int dyf_abi_version(void);
+const char* dyf_last_error(void);
+/* Number of CUDA kernels the engine has launched in this process (for bench.py's `gpu_launches`). */
+uint64_t dyf_launch_count(void);
+
+/* Replaces: `hydra.utils.instantiate(model_config, ...)` -> backbone constructor
+ * (src/experiment_types/_base_experiment.py:180-188). */
+int dyf_net_create(const dyf_net_desc* desc, dyf_net** out);
+void dyf_net_destroy(dyf_net* net);
+
+/* Replaces: `nn.Module.load_state_dict` for one tensor.  `key` is the reference's state-dict key,
+ * `data` a device pointer to fp32 (int64 `num_batches_tracked` entries are accepted and ignored), `shape/ndim`
+ * the tensor's shape.  Unknown keys and shape mismatches are errors (strict loading). */
+int dyf_net_set_param(dyf_net* net, const char* key, const void* data, const int64_t* shape, int32_t ndim);
+
+/* Folds eval-mode BatchNorm / weight standardisation, re-packs weights to the kernel layouts (bf16, KRSC).
+ * Must be called after all parameters are set and again after any parameter changes.  Fails, naming the first
+ * missing key, if a parameter was never set. */
+int dyf_net_finalize(dyf_net* net, void* stream);
+
+/* Number of state-dict keys the backbone expects and the i-th key (for strictness checks on the host). */
+int dyf_net_num_params(const dyf_net* net);
+const char* dyf_net_param_key(const dyf_net* net, int32_t i);
+/* Shape of the i-th parameter (`shape` receives up to 4 extents); returns ndim, or <0 on error.  `is_buffer` is set
+ * for BatchNorm running statistics / num_batches_tracked (nn.Module buffers rather than parameters). */
+int dyf_net_param_shape(const dyf_net* net, int32_t i, int64_t* shape, int32_t* is_buffer);
+
+int dyf_net_workspace_bytes(const dyf_net* net, int32_t rows, size_t* bytes);
+
+/* Replaces: backbone `forward(inputs, time=, condition=)` (src/models/unet_simple.py:181-197, src/models/unet.py:266-315,
+ * src/models/simple_conv_net.py:112-131).  x: [rows, in_channels, H, W]; cond: [rows, cond_channels, H, W] or NULL when
+ * cond_channels == 0; time: [rows] fp32 or NULL when with_time_emb == 0; y: [rows, out_channels, H, W]. */
+int dyf_net_forward(dyf_net* net, int32_t rows, const float* x, const float* cond, const float* time, float* y,
+                    const dyf_dropout* drop, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with the channel concatenation expressed as a list of source tensors in concat order (each
+ * [rows, src_channels[i], H, W]); lets the sampler skip the reference's torch.cat calls
+ * (src/diffusion/dyffusion.py:189, :488; src/models/unet_simple.py:184). */
+int dyf_net_forward_srcs(dyf_net* net, int32_t rows, const float* const* srcs, const int32_t* src_channels,
+                         int32_t nsrc, const float* time, float* y, const dyf_dropout* drop, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Sampler description = the DYffusion hyper-parameters that `sample_loop` reads (src/diffusion/dyffusion.py:18-95,
+ * :335-426).  The schedule is passed already parsed: `schedule[i]` = diffusion step s_i (may be fractional),
+ * `tau[i]` = diffusion_step_to_interpolation_step(s_i) (:101-138); both computed on the host by the drop-in class. */
+typedef struct dyf_sampler_desc {
+  int32_t num_timesteps;          /* N (after auxiliary steps) */
+  int32_t n_schedule;
+  const double* schedule;         /* HOST pointer, n_schedule entries */
+  const double* tau;              /* HOST pointer, n_schedule entries */
+  const double* time_forecaster;  /* HOST pointer, n_schedule entries: time fed to the forecaster (time_encoding) */
+  int32_t forward_conditioning;   /* 0 = "none", 1 = "data", 2 = "data+noise" (:205-239) */
+  int32_t sampling_type;          /* 0 = "cold", 1 = "naive" (:381-393) */
+  int32_t use_cold_sampling_for_last_step;
+  int32_t n_refine;               /* number of refinement times (0 = refine_intermediate_predictions False) */
+  const double* refine_times;     /* HOST pointer (:408-422) */
+  int32_t enable_interpolator_dropout; /* (:154) */
+  int32_t channels;               /* C = forecaster in_channels */
+  int32_t window_channels;        /* channels of `initial_condition` (C * window) */
+  int32_t static_channels;        /* channels of `static_condition` (0 = None) */
+  int32_t interpolator_horizon;   /* for the 0 < t < horizon check (:484-486) */
+  int32_t max_rows_per_call;      /* cap on rows per backbone launch when calls are batched (0 = default) */
+} dyf_sampler_desc;
+
+int dyf_sampler_create(dyf_net* forecaster, dyf_net* interpolator, const dyf_sampler_desc* desc, dyf_sampler** out);
+void dyf_sampler_destroy(dyf_sampler* s);
+int dyf_sampler_workspace_bytes(const dyf_sampler* s, int32_t rows, size_t* bytes);
+/* Number of output slots (`preds` holds n_outputs tensors of [rows, C, H, W]); slot j carries the forecast whose
+ * reference key is "t{out_key[j]}_preds"; keys[] is filled with n_outputs doubles. */
+int dyf_sampler_num_outputs(const dyf_sampler* s, int32_t* n_outputs, double* keys, int32_t keys_capacity);
+
+/* Replaces: `BaseDYffusion.sample_loop` / `sample` (src/diffusion/dyffusion.py:335-431).
+ * ic: [rows, window_channels, H, W]; static_cond: [rows, static_channels, H, W] or NULL;
+ * preds: [n_outputs, rows, C, H, W] fp32; x0_hat_out (optional): final forecaster output [rows, C, H, W]. */
+int dyf_sampler_run(dyf_sampler* s, int32_t rows, const float* ic, const float* static_cond, float* preds,
+                    float* x0_hat_out, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook: writes the keep-mask (1/0 bytes) the engine's dropout draws for a tensor of `n_elems` elements
+ * (NHWC element order, channel count `channels`) at (seed, stream, site, p).  Lets tests replay engine masks in
+ * the oracle. */
+int dyf_debug_dropout_mask(uint64_t seed, uint64_t stream, uint32_t site, float p, int64_t n_elems, uint8_t* mask,
+                           void* stream_handle);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYFFUSION_B200_H */
