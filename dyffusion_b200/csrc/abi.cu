@@ -1,6 +1,7 @@
 // extern "C" surface of the engine (include/dyffusion_b200.h).
 #include <atomic>
 #include <new>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -10,6 +11,28 @@ static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- launch profiler
+struct ProfRec { cudaEvent_t a, b; int klass; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(cudaStream_t stream, int klass, double flops, double bytes) : s(stream), idx(-1) {
+  if (!g_prof_on) return;
+  ProfRec r{take_event(), take_event(), klass, flops, bytes};
+  cudaEventRecord(r.a, s);
+  idx = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].b, s);
+}
 }  // namespace dyf
 
 using namespace dyf;
@@ -29,6 +52,29 @@ extern "C" {
 int dyf_abi_version(void) { return DYF_ABI_VERSION; }
 const char* dyf_last_error(void) { return get_error(); }
 uint64_t dyf_launch_count(void) { return g_launches.load(); }
+
+int dyf_profile_enable(int32_t on) {
+  if (!on) {
+    for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+    g_prof.clear();
+  }
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int dyf_profile_read(double* ms, double* flops, double* bytes, uint64_t* launches, int32_t n_classes) {
+  if (!ms || !flops || !bytes || !launches || n_classes < KC_COUNT) { set_error("bad argument"); return DYF_ERR_ARG; }
+  for (int i = 0; i < n_classes; ++i) { ms[i] = flops[i] = bytes[i] = 0.0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { set_error("profile: event sync failed"); return DYF_ERR_CUDA; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { set_error("profile: elapsed failed"); return DYF_ERR_CUDA; }
+    ms[r.klass] += t; flops[r.klass] += r.flops; bytes[r.klass] += r.bytes; launches[r.klass] += 1;
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int dyf_net_create(const dyf_net_desc* desc, dyf_net** out) {
   if (!desc || !out) { set_error("null argument"); return DYF_ERR_ARG; }

@@ -397,6 +397,7 @@ __global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
 int launch_pack(const PackParams& p, cudaStream_t s) {
   if (p.Cpad % 8 != 0) { set_error("pack: Cpad must be a multiple of 8"); return -1; }
   const long long total = (long long)p.rows * p.Ho * p.Wo;
+  ProfScope prof(s, KC_PACK);
   pack_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("pack_kernel");
   return 0;
@@ -405,6 +406,7 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
 int launch_upsample(const UpsampleParams& p, cudaStream_t s) {
   if ((p.C[0] | p.C[1] | p.ld[0] | p.ld[1]) & 7) { set_error("upsample: channel counts must be multiples of 8"); return -1; }
   const long long total = (long long)p.rows * p.H * p.scale * p.W * p.scale * ((p.C[0] + p.C[1]) >> 3);
+  ProfScope prof(s, KC_UPSAMPLE, 0.0, 2.0 * 1.25 * (double)total * 8);
   upsample_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("upsample_kernel");
   return 0;
@@ -420,6 +422,7 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
   const int pstep = 256 / chunks;
   int pix_per_block = pstep * 16;
   dim3 grid(cdiv(p.HW, pix_per_block), p.rows);
+  ProfScope prof(s, KC_GROUPNORM);
   groupnorm_stats_kernel<<<grid, 256, 0, s>>>(p, pix_per_block);
   DYF_LAUNCH_OK("groupnorm_stats_kernel");
   const long long total = (long long)p.rows * p.HW * chunks;
@@ -436,6 +439,7 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s) {
   }
   const long long total = (long long)p.rows * p.Ho * p.Wo * lanes;
   const size_t smem = (size_t)16 * p.Cout * p.Cin * sizeof(float);
+  ProfScope prof(s, KC_READOUT);
   readout_kernel<<<cdiv(total, 256), 256, smem, s>>>(p);
   DYF_LAUNCH_OK("readout_kernel");
   return 0;
@@ -445,6 +449,7 @@ int launch_time_tables(const TimeParams& p, cudaStream_t s) {
   if (p.dim > 256 || p.time_dim > 512) { set_error("time tables: dim too large"); return -1; }
   if (p.n_layers == 0) return 0;
   dim3 grid(p.n_layers, p.rows);
+  ProfScope prof(s, KC_TIME);
   time_tables_kernel<<<grid, 128, 0, s>>>(p);
   DYF_LAUNCH_OK("time_tables_kernel");
   return 0;
@@ -465,11 +470,13 @@ int launch_fold_norm(const float* bias, const float* g, const float* beta, const
 }
 
 int launch_cold_update(float* x_s, const float* a, const float* b, float* out, long long n, cudaStream_t s) {
+  ProfScope prof(s, KC_ELEMENTWISE);
   cold_update_kernel<<<cdiv(n, 256), 256, 0, s>>>(x_s, a, b, out, n);
   DYF_LAUNCH_OK("cold_update_kernel");
   return 0;
 }
 int launch_fill(float* p, float v, long long n, cudaStream_t s) {
+  ProfScope prof(s, KC_ELEMENTWISE);
   fill_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, v, n);
   DYF_LAUNCH_OK("fill_kernel");
   return 0;

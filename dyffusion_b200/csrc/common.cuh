@@ -13,6 +13,17 @@ void set_error(const std::string& msg);
 const char* get_error();
 void count_launch(int n = 1);
 
+// Optional per-launch CUDA-event bracketing (bench.py's roofline measurement): when enabled, every kernel launch
+// is timed on its own stream and accumulated per kernel class.
+enum KernelClass : int { KC_CONV_MMA = 0, KC_CONV_UMMA, KC_PACK, KC_UPSAMPLE, KC_GROUPNORM, KC_READOUT, KC_TIME,
+                         KC_ELEMENTWISE, KC_ATTENTION, KC_COUNT };
+struct ProfScope {
+  cudaStream_t s;
+  int idx;
+  ProfScope(cudaStream_t stream, int klass, double flops = 0.0, double bytes = 0.0);
+  ~ProfScope();
+};
+
 #define DYF_CUDA_OK(expr)                                                                              \
   do {                                                                                                 \
     cudaError_t _e = (expr);                                                                           \

@@ -14,6 +14,7 @@ struct ConvParams {
   const float* tabB;         // [rows, Cout]
   const __nv_bfloat16* res;  // optional residual added after activation+dropout, [M, res_ld]
   int rows, Hi, Wi, Cin;
+  int Cin_real;              // un-padded input channels (FLOP accounting only)
   int Ho, Wo, Cout;
   int KH, KW, stride, pad;
   int K, Kpad;

@@ -171,6 +171,9 @@ int launch(const ConvParams& p, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.Cout + BN - 1) / BN));
+  const double flops = 2.0 * (double)p.M * p.Cout * p.KH * p.KW * p.Cin_real;
+  const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
+  ProfScope prof(stream, KC_CONV_MMA, flops, bytes);
   conv_mma_kernel<BN><<<grid, THREADS, smem, stream>>>(p);
   DYF_LAUNCH_OK("conv_mma_kernel");
   return 0;

@@ -377,7 +377,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         const Buf& bi = bufs[o.in0];
         ConvParams p{};
         p.in = bp[o.in0]; p.w = wq + c.wq_off;
-        p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C;
+        p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C; p.Cin_real = c.Cin;
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
         p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;

@@ -74,6 +74,9 @@ def _load() -> C.CDLL:
         "dyf_sampler_num_outputs": (C.c_int, [vp, C.POINTER(i32), C.POINTER(C.c_double), i32]),
         "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, vp, sz, vp]),
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
+        "dyf_profile_enable": (C.c_int, [i32]),
+        "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(u64), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -88,7 +91,9 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_net_set_param", "dyf_net_finalize", "dyf_net_num_params", "dyf_net_param_key", "dyf_net_param_shape",
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
-            "dyf_debug_dropout_mask"]
+            "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_read"]
+KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
+                  "attention"]
 
 
 class EngineError(RuntimeError):
@@ -107,6 +112,18 @@ def _check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(LIB.dyf_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    _check(LIB.dyf_profile_enable(int(bool(on))))
+
+
+def profile_read() -> Dict[str, Dict[str, float]]:
+    """Per kernel class: device ms (CUDA events around every launch), algorithmic FLOPs / bytes, launch count."""
+    n = len(KERNEL_CLASSES)
+    ms, fl, by, la = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
+    _check(LIB.dyf_profile_read(ms, fl, by, la, n))
+    return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(la[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
 
 def _stream_ptr() -> int:

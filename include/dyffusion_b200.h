@@ -86,6 +86,15 @@ const char* dyf_last_error(void);
 /* Number of CUDA kernels the engine has launched in this process (for bench.py's `gpu_launches`). */
 uint64_t dyf_launch_count(void);
 
+/* Measurement hooks (bench.py): while enabled, every engine kernel launch is bracketed by CUDA events on its own
+ * stream.  `dyf_profile_read` waits for the recorded events and returns, per kernel class (DYF_KC_*), the summed
+ * device time [ms], algorithmic FLOPs, algorithmic bytes and launch count since the last read; arrays must hold
+ * DYF_KC_COUNT entries. */
+enum { DYF_KC_CONV_MMA = 0, DYF_KC_CONV_UMMA, DYF_KC_PACK, DYF_KC_UPSAMPLE, DYF_KC_GROUPNORM, DYF_KC_READOUT,
+       DYF_KC_TIME, DYF_KC_ELEMENTWISE, DYF_KC_ATTENTION, DYF_KC_COUNT };
+int dyf_profile_enable(int32_t on);
+int dyf_profile_read(double* ms, double* flops, double* bytes, uint64_t* launches, int32_t n_classes);
+
 /* Replaces: `hydra.utils.instantiate(model_config, ...)` -> backbone constructor
  * (src/experiment_types/_base_experiment.py:180-188). */
 int dyf_net_create(const dyf_net_desc* desc, dyf_net** out);
