@@ -8,6 +8,7 @@ namespace dyf {
 
 struct ConvParams {
   const __nv_bfloat16* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
+  const __nv_bfloat16* w_umma;  // weights re-packed as UMMA stage tiles (conv_umma.cu) or nullptr
   const __nv_bfloat16* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
   void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32
   const float* tabA;         // [rows, Cout]  y = acc * A + B   (folded norm, conv bias, time scale/shift)
@@ -88,5 +89,7 @@ int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
 // pipeline), <0 on error.
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 bool conv_umma_eligible(const ConvParams& p);
+bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad);
+int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int standardize, cudaStream_t s);
 
 }  // namespace dyf

@@ -28,6 +28,7 @@ struct ConvLayer {
   bool standardize = false;                   // WeightStandardizedConv2d
   int K = 0, Kpad = 0;
   size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
+  long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
   int table = -1;                             // index into Net::time_layers
 };
@@ -75,9 +76,10 @@ struct Net {
   long long tab_floats_per_row = 0;    // sum of C over time_layers
   long long stats_floats_per_row = 0;
   long long packed_floats = 0, extra_floats = 0;
-  size_t wq_elems = 0;
+  size_t wq_elems = 0, wu_elems = 0;
   float* packed = nullptr;             // device: all fp32 params + folded vectors
   __nv_bfloat16* wq = nullptr;         // device: packed bf16 conv weights
+  __nv_bfloat16* wq_umma = nullptr;    // device: weights of tcgen05-eligible layers as UMMA stage tiles
   TimeLayer* d_time_layers = nullptr;  // device copy
   bool finalized = false;
   int Hin = 0, Win = 0;                // network grid (after the optional outer resize)

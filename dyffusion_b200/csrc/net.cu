@@ -1,6 +1,7 @@
 // Backbone plans: parameter bookkeeping (reference state-dict keys), weight folding/re-packing, and the per-forward
 // kernel sequence of the three hot-path networks.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -12,6 +13,7 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 Net::~Net() {
   if (packed) cudaFree(packed);
   if (wq) cudaFree(wq);
+  if (wq_umma) cudaFree(wq_umma);
   if (d_time_layers) cudaFree(d_time_layers);
 }
 
@@ -52,6 +54,10 @@ int Net::add_conv(const std::string& prefix, int Cin, int Cout, int k, int strid
   if (bias) c.b = add_param(prefix + ".bias", {Cout});
   c.wq_off = wq_elems;
   wq_elems += (size_t)Cout * c.Kpad;
+  if (conv_umma_shape_ok(c.Cpad, Cout, k, stride, pad) && c.Cpad == Cin) {
+    c.wu_off = (long long)wu_elems;
+    wu_elems += (size_t)Cout * Cin * 9;
+  }
   c.na_off = packed_floats + extra_floats;  // resolved against the final packed size in finalize()
   extra_floats += round_up(Cout, 4);
   c.nb_off = packed_floats + extra_floats;
@@ -281,7 +287,12 @@ int Net::finalize(cudaStream_t s) {
   for (auto& p : params)
     if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
   if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
+  if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
   for (auto& c : convs) {
+    if (c.wu_off >= 0) {
+      int rcu = launch_repack_umma(packed + params[c.w].off, wq_umma + c.wu_off, c.Cout, c.Cin, c.standardize ? 1 : 0, s);
+      if (rcu) return rcu;
+    }
     int rc = launch_repack_conv(packed + params[c.w].off, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
                                 c.standardize ? 1 : 0, s);
     if (rc) return rc;
@@ -377,6 +388,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         const Buf& bi = bufs[o.in0];
         ConvParams p{};
         p.in = bp[o.in0]; p.w = wq + c.wq_off;
+        p.w_umma = (c.wu_off >= 0 && !getenv("DYF_DISABLE_UMMA")) ? wq_umma + c.wu_off : nullptr;
         p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C; p.Cin_real = c.Cin;
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
