@@ -24,7 +24,7 @@ constexpr int PATCH_H = TILE_H + 2, PATCH_W = TILE_W + 2;
 constexpr int PATCH_PIX = PATCH_H * PATCH_W;    // 180
 constexpr int A_PLANE = (PATCH_PIX + 1) * 16;   // bytes per 8-channel plane; odd pixel pitch => conflict-free fills
 constexpr int A_STAGE = 8 * A_PLANE;            // one 64-channel chunk
-constexpr int A_STAGES = 2, B_STAGES = 4;
+constexpr int A_STAGES = 2, B_STAGES = 3;
 constexpr int THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {  // arrive when this thread's prior cp.async land
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -80,6 +83,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
@@ -105,6 +114,7 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_STAGES * A_STAGE;
   Barriers* bars = reinterpret_cast<Barriers*>(sB + B_STAGES * B_STAGE);
+  float* s_tab = reinterpret_cast<float*>(bars + 1);  // [2][BN]: epilogue multiplier / offset of this (row, n_tile)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tile = blockIdx.y;
@@ -124,6 +134,10 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
   if (warp == 4) {  // TMEM allocation (power of two >= 32 columns), owned by this warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (warp == 5) {  // per-(row, channel) epilogue tables: one batch row per tile, so a plain smem copy suffices
+    const size_t tb = (size_t)row * p.Cout + n_tile * BN;
+    for (int i = lane; i < BN; i += 32) { s_tab[i] = __ldg(p.tabA + tb + i); s_tab[BN + i] = __ldg(p.tabB + tb + i); }
   }
   tc_fence_before();
   __syncthreads();
@@ -148,6 +162,7 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
       src_off[it] = off;
     }
     const __nv_bfloat16* in_row = p.in + (size_t)row * p.Hi * p.Wi * p.Cin + chunk8 * 8;
+    const __nv_bfloat16* const in_base = p.in;
     for (int c = 0; c < nchunks; ++c) {
       const int st = c % A_STAGES;
       mbar_wait(smem_u32(&bars->a_empty[st]), ((c / A_STAGES) & 1) ^ 1);
@@ -157,19 +172,13 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
         const int pix = (tid >> 3) + it * 16;
         if (pix < PATCH_PIX) {
           const bool v = src_off[it] >= 0;
-          cp_async16(dst0 + pix * 16, v ? (const void*)(in_row + src_off[it] + c * 64) : (const void*)p.in, v ? 16 : 0);
+          cp_async16(dst0 + pix * 16, v ? (const void*)(in_row + src_off[it] + c * 64) : (const void*)in_base, v ? 16 : 0);
         }
       }
-      cp_async_commit();
-      if (c >= 1) {  // the previous chunk has landed: publish it to the tensor core (async proxy)
-        cp_async_wait<1>();
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&bars->a_full[(c - 1) % A_STAGES]));
-      }
+      // hardware arrives on a_full[st] once this thread's copies have landed (no wait, no proxy fence needed:
+      // same pattern as CUTLASS's sm100 cp.async mainloop); the producer immediately moves on to the next chunk
+      cp_async_arrive_noinc(smem_u32(&bars->a_full[st]));
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(smem_u32(&bars->a_full[(nchunks - 1) % A_STAGES]));
 
     // =============================== epilogue: TMEM -> registers -> fused math -> global ===========================
     mbar_wait(smem_u32(&bars->acc_full), 0);
@@ -178,17 +187,51 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
     const int oy = oy0 + (m_local >> 3), ox = ox0 + (m_local & 7);
     const bool valid = oy < p.Ho && ox < p.Wo;
     const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
-#pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + cb, v);
-      if (valid) {
+    __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
+    const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+    const int act = p.act;
+    const uint32_t thresh = p.drop.thresh;
+    const float dscale = p.drop.scale;
+#pragma unroll 2
+    for (int c0 = 0; c0 < BN; c0 += 8) {
+      {
+        uint32_t v[8];
+        tmem_ld8(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, v);
+        float y[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float a8[8];
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[j]), s_tab[c0 + j], s_tab[BN + c0 + j]);
+        switch (act) {
+          case ACT_RELU:
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(v[g * 8 + j]);
-          conv_epilogue8(p, m, n_tile * BN + cb + g * 8, a8);
+            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+            break;
+          case ACT_LEAKY:
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.2f * y[j];
+            break;
+          case ACT_SILU:
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = y[j] / (1.f + __expf(-y[j]));
+            break;
+          case ACT_GELU:
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = 0.5f * y[j] * (1.f + erff(y[j] * 0.70710678118654752f));
+            break;
+          default: break;
+        }
+        if (thresh) {
+          const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + n_tile * BN + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = ((keep >> j) & 1u) ? y[j] * dscale : 0.f;
+        }
+        if (valid) {
+          if (rrow) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] += f[j];
+          }
+          *reinterpret_cast<uint4*>(orow + c0) = pack8(y);
         }
       }
     }
@@ -272,7 +315,7 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 
 template <int BN>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  constexpr int smem = A_STAGES * A_STAGE + B_STAGES * BN * 128 + (int)sizeof(Barriers) + 64;
+  constexpr int smem = A_STAGES * A_STAGE + B_STAGES * BN * 128 + (int)sizeof(Barriers) + 2 * BN * 4 + 64;
   static bool configured = false;
   if (!configured) {
     DYF_CUDA_OK(cudaFuncSetAttribute(conv3x3_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
