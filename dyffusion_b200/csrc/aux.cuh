@@ -15,11 +15,24 @@ struct PackParams {
   int bilinear;            // 0 = same size copy, 1 = bilinear resize Hi x Wi -> Ho x Wo
   __nv_bfloat16* out;
   // "data+noise" forecaster conditioning (dyffusion.py:220-227): src[noise_src] <- w*src + (1-w)*N(0,1)
+  int ones_channel;        // output channel set to 1.0 inside the image (carries a folded bias), -1 = none
   int noise_src;           // -1 = none
   float noise_w;
   uint64_t seed, stream;
 };
 int launch_pack(const PackParams& p, cudaStream_t s);
+
+// ---- fused stem of unet_simple: [bilinear resize ->] 1x1 conv (C_in <= 16 -> 64) + bias [+ input dropout],
+//      fp32 NCHW sources -> bf16 NHWC, never materialising the resized input (reference unet_simple.py:193 + :113-116)
+struct StemParams {
+  PackParams pk;           // sources / geometry (pk.out and pk.Cpad unused)
+  const float* w;          // [Cout, Cin] fp32 (Conv2d 1x1 weight)
+  const float* bias;       // [Cout]
+  __nv_bfloat16* out;      // [rows, Ho, Wo, Cout]
+  int Cin, Cout;
+  DropCfg drop;
+};
+int launch_stem(const StemParams& p, cudaStream_t s);
 
 // ---- x2 upsample (bilinear align_corners=False | nearest) of up to two bf16 NHWC sources into one concat buffer
 struct UpsampleParams {
@@ -42,8 +55,10 @@ struct GroupNormParams {
   const float* tabA;        // [rows, C] (scale + 1) or nullptr
   const float* tabB;        // [rows, C] shift or nullptr
   const __nv_bfloat16* res; // optional residual [rows, HW, res_ld], added last
-  float* stats;             // [rows, G, 2] scratch (zeroed by the launcher)
+  float* stats;             // [rows, G, 32 slabs, 2] scratch: per-slab partial sums, combined in fixed order
+  int slabs;                // set by the launcher
   int rows, HW, C, G, res_ld;
+  int tab_div;              // table row = r / tab_div
   int act;
   float eps;
   DropCfg drop;
@@ -81,6 +96,8 @@ struct TimeParams {
   int rows;
   float* tabA;            // per layer: [rows, C] at rows * tab_off
   float* tabB;
+  float* temb;            // scratch [rows, time_dim]: SiLU(time embedding)
+  int total_ch;           // padded channel count over all layers (= floats per row of tabA)
 };
 int launch_time_tables(const TimeParams& p, cudaStream_t s);
 
@@ -88,6 +105,10 @@ int launch_time_tables(const TimeParams& p, cudaStream_t s);
 // conv weight fp32 [O, I, KH, KW] -> bf16 [O, Kpad], k = (ky*KW+kx)*Cpad + c; optional weight standardisation
 int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
                        int standardize, cudaStream_t s);
+// composite weight of (1x1 conv Wi,bi : Cs -> Cm) followed by (conv W0 : Cm -> O, KHxKW): bf16 [O, Kpad] over Cs real
+// channels + one "ones" channel carrying bi (zero outside the image, like the padded 1x1 output)
+int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_bfloat16* out, int O, int Cm, int Cs,
+                        int KH, int KW, int Cpad, int Kpad, cudaStream_t s);
 // folded affine of conv-bias + eval BatchNorm: na = g*rsqrt(var+eps), nb = (bias-mean)*na + beta (bn may be null)
 int launch_fold_norm(const float* bias, const float* g, const float* beta, const float* mean, const float* var,
                      float eps, float* na, float* nb, int C, cudaStream_t s);

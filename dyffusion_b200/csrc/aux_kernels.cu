@@ -62,8 +62,81 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
     }
   }
   while (oc < p.Cpad) {
-    v[oc & 7] = 0.f;
+    v[oc & 7] = oc == p.ones_channel ? 1.f : 0.f;
     if ((++oc & 7) == 0) *reinterpret_cast<uint4*>(o + oc - 8) = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused stem
+// One warp = 32 consecutive output pixels.  Phase 1: lane p gathers (bilinear) the C_in input values of pixel p --
+// neighbouring lanes read neighbouring source addresses of the same channel plane, so the gathers coalesce.
+// Phase 2: lane p computes the 64 output channels of its pixel (fp32), the warp stages them in shared memory and
+// writes the 32 x 128-byte pixel lines with fully coalesced 128-bit stores.
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+  __shared__ __align__(16) float s_w[16 * 64];      // [c][o]
+  __shared__ float s_b[64];
+  __shared__ __align__(16) uint4 s_out[8][32 * 9];  // per warp: 32 pixels x 8 chunks (+1 pad)
+  for (int i = threadIdx.x; i < p.Cin * 64; i += blockDim.x) s_w[i] = p.w[(size_t)(i & 63) * p.Cin + (i >> 6)];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_b[i] = p.bias[i];
+  __syncthreads();
+  const PackParams& k = p.pk;
+  const long long total = (long long)k.rows * k.Ho * k.Wo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pix0 = ((long long)blockIdx.x * 8 + warp) * 32;
+  const long long pix = pix0 + lane;
+  const bool active = pix < total;
+  const long long pp = active ? pix : 0;
+  const int ox = (int)(pp % k.Wo);
+  const int oy = (int)((pp / k.Wo) % k.Ho);
+  const int r = (int)(pp / ((long long)k.Wo * k.Ho));
+  int y0 = oy, y1 = oy, x0 = ox, x1 = ox;
+  float ly = 0.f, lx = 0.f;
+  if (k.bilinear) {
+    bilinear_coord(oy, k.Hi, (float)k.Hi / (float)k.Ho, y0, y1, ly);
+    bilinear_coord(ox, k.Wi, (float)k.Wi / (float)k.Wo, x0, x1, lx);
+  }
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const size_t plane = (size_t)k.Hi * k.Wi;
+  const size_t o00 = (size_t)y0 * k.Wi + x0, o01 = (size_t)y0 * k.Wi + x1, o10 = (size_t)y1 * k.Wi + x0,
+               o11 = (size_t)y1 * k.Wi + x1;
+  float acc[64];
+#pragma unroll
+  for (int o = 0; o < 64; ++o) acc[o] = s_b[o];
+  int c = 0;
+  for (int s = 0; s < k.nsrc; ++s) {
+    const float* base = k.src[s] + (size_t)(r % k.src_rows) * k.C[s] * plane;
+    for (int cc = 0; cc < k.C[s]; ++cc, ++c) {
+      const float* pl = base + (size_t)cc * plane;
+      const float v = k.bilinear ? w00 * __ldg(pl + o00) + w01 * __ldg(pl + o01) + w10 * __ldg(pl + o10) + w11 * __ldg(pl + o11)
+                                 : __ldg(pl + o00);
+      const float4* wr = reinterpret_cast<const float4*>(s_w + c * 64);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 w4 = wr[q];
+        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (p.drop.thresh) {
+      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pp * 64 + g * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g * 8 + e] = ((keep >> e) & 1u) ? acc[g * 8 + e] * p.drop.scale : 0.f;
+    }
+    s_out[warp][lane * 9 + g] = pack8(acc + g * 8);
+  }
+  __syncwarp();
+  // coalesced write-out: 32 pixels x 128 B are contiguous in the NHWC output
+  uint4* out = reinterpret_cast<uint4*>(p.out + (size_t)pix0 * 64);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int q = it * 32 + lane;  // 16-byte unit inside the warp's 4 KB span
+    const int pl_ = q >> 3, g = q & 7;
+    if (pix0 + pl_ < total) out[q] = s_out[warp][pl_ * 9 + g];
   }
 }
 
@@ -107,15 +180,74 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
   *reinterpret_cast<uint4*>(p.out + (size_t)pix * Ct + c) = outv;
 }
 
+// Bilinear x2 (align_corners=False) as a fixed separable stencil: with source indices clamped to the image,
+//   u[2i] = 0.25 x[i-1] + 0.75 x[i],   u[2i+1] = 0.75 x[i] + 0.25 x[i+1]
+// (identical to PyTorch's coordinate rule, including the clamped first/last rows).  One thread turns the 3 x 3 source
+// neighbourhood of pixel (i, j) into the 2 x 2 output quad for 8 channels: 9 independent 128-bit loads, 4 stores.
+__global__ void __launch_bounds__(256) upsample2x_quad_kernel(const UpsampleParams p) {
+  const int Ct = p.C[0] + p.C[1];
+  const int chunks = Ct >> 3;
+  const long long total = (long long)p.rows * p.H * p.W * chunks;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  const long long pix = idx / chunks;
+  const int j = (int)(pix % p.W);
+  const int i = (int)((pix / p.W) % p.H);
+  const int r = (int)(pix / ((long long)p.W * p.H));
+  const int c = ch << 3;
+  const int s = c < p.C[0] ? 0 : 1;
+  const int cs = s ? c - p.C[0] : c;
+  const int ld = p.ld[s];
+  const __nv_bfloat16* src = p.src[s] + (size_t)r * p.H * p.W * ld + cs;
+  const int ym = max(i - 1, 0), yp = min(i + 1, p.H - 1), xm = max(j - 1, 0), xp = min(j + 1, p.W - 1);
+  const int ys[3] = {ym, i, yp};
+  uint4 raw[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const __nv_bfloat16* rowp = src + (size_t)ys[a] * p.W * ld;
+    raw[a][0] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xm * ld));
+    raw[a][1] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)j * ld));
+    raw[a][2] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xp * ld));
+  }
+  float h0[3][8], h1[3][8];  // horizontally interpolated: columns 2j and 2j+1
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float L[8], C[8], R[8];
+    unpack8(raw[a][0], L); unpack8(raw[a][1], C); unpack8(raw[a][2], R);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      h0[a][e] = 0.25f * L[e] + 0.75f * C[e];
+      h1[a][e] = 0.75f * C[e] + 0.25f * R[e];
+    }
+  }
+  float o[8];
+  const int Wo = 2 * p.W;
+  __nv_bfloat16* out = p.out + (((size_t)r * 2 * p.H + 2 * i) * Wo + 2 * j) * Ct + c;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.25f * h0[0][e] + 0.75f * h0[1][e];
+  *reinterpret_cast<uint4*>(out) = pack8(o);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.25f * h1[0][e] + 0.75f * h1[1][e];
+  *reinterpret_cast<uint4*>(out + Ct) = pack8(o);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.75f * h0[1][e] + 0.25f * h0[2][e];
+  *reinterpret_cast<uint4*>(out + (size_t)Wo * Ct) = pack8(o);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.75f * h1[1][e] + 0.25f * h1[2][e];
+  *reinterpret_cast<uint4*>(out + (size_t)Wo * Ct + Ct) = pack8(o);
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// pass 1: per (row, group) sum / sum of squares.  Each thread owns one fixed 8-channel chunk => one fixed group.
+// pass 1: per (row, group, pixel-slab) sum / sum of squares, reduced in a FIXED order (no float atomics), so that the
+// statistics -- and with them every downstream bf16 rounding -- are bit-reproducible from run to run.
+// Each thread owns one fixed 8-channel chunk => one fixed group.  Partials land in stats[row][group][slab][2].
+constexpr int GN_SLABS = 32;
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormParams p, int pix_per_block) {
-  __shared__ float s_acc[64][2];
+  __shared__ float s_part[256][2];
   const int r = blockIdx.y;
   const int chunks = p.C >> 3;
   const int cpg = p.C / p.G;  // channels per group (multiple of 8)
-  for (int i = threadIdx.x; i < p.G; i += blockDim.x) s_acc[i][0] = s_acc[i][1] = 0.f;
-  __syncthreads();
   const int ch = threadIdx.x % chunks;
   const int pstep = blockDim.x / chunks;
   const int p0 = blockIdx.x * pix_per_block;
@@ -128,13 +260,17 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormPar
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
   }
-  const int g = (ch << 3) / cpg;
-  atomicAdd(&s_acc[g][0], s1);
-  atomicAdd(&s_acc[g][1], s2);
+  s_part[threadIdx.x][0] = s1;
+  s_part[threadIdx.x][1] = s2;
   __syncthreads();
-  for (int i = threadIdx.x; i < p.G; i += blockDim.x) {
-    atomicAdd(p.stats + ((size_t)r * p.G + i) * 2 + 0, s_acc[i][0]);
-    atomicAdd(p.stats + ((size_t)r * p.G + i) * 2 + 1, s_acc[i][1]);
+  if (threadIdx.x < p.G) {  // thread g sums the partials of group g in thread order
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int t = 0; t < (int)blockDim.x; ++t)
+      if (((t % chunks) << 3) / cpg == g) { a += s_part[t][0]; b += s_part[t][1]; }
+    float* o = p.stats + (((size_t)r * p.G + g) * GN_SLABS + blockIdx.x) * 2;
+    o[0] = a;
+    o[1] = b;
   }
 }
 
@@ -151,15 +287,18 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormPar
   const int cpg = p.C / p.G;
   const int g = c0 / cpg;
   const float n = (float)p.HW * (float)cpg;
-  const float mean = p.stats[((size_t)r * p.G + g) * 2] / n;
-  const float var = fmaxf(p.stats[((size_t)r * p.G + g) * 2 + 1] / n - mean * mean, 0.f);
+  float sum1 = 0.f, sum2 = 0.f;
+  const float* st = p.stats + ((size_t)r * p.G + g) * GN_SLABS * 2;
+  for (int sl = 0; sl < p.slabs; ++sl) { sum1 += st[2 * sl]; sum2 += st[2 * sl + 1]; }  // fixed order
+  const float mean = sum1 / n;
+  const float var = fmaxf(sum2 / n - mean * mean, 0.f);
   const float rstd = rsqrtf(var + p.eps);
   float f[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.C + c0)), f);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float v = (f[j] - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
-    if (p.tabA) v = v * __ldg(p.tabA + (size_t)r * p.C + c0 + j) + __ldg(p.tabB + (size_t)r * p.C + c0 + j);
+    if (p.tabA) v = v * __ldg(p.tabA + (size_t)(r / p.tab_div) * p.C + c0 + j) + __ldg(p.tabB + (size_t)(r / p.tab_div) * p.C + c0 + j);
     f[j] = apply_act(v, p.act);
   }
   if (p.drop.thresh) {
@@ -205,30 +344,34 @@ __global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
   const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
   float acc[RO_MAXC] = {0.f, 0.f, 0.f, 0.f};
   const __nv_bfloat16* xr = p.x + (size_t)r * p.Hs * p.Ws * p.Cin + (sub << 3);
+  // 2 x 2 bilinear corners x 2 x 2 transposed-conv taps, all 16 combinations executed by every lane (no divergence):
+  // invalid taps get weight 0 and a clamped address.
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const float wgt = wy[a] * wx[b];
-      if (wgt == 0.f) continue;
       const int yy = Y[a], xx = X[b];
-      for (int ky = (yy + 1) & 1; ky < 4; ky += 2) {
-        const int iy = (yy + 1 - ky) >> 1;
-        if (iy < 0 || iy >= p.Hs) continue;
-        for (int kx = (xx + 1) & 1; kx < 4; kx += 2) {
-          const int ix = (xx + 1 - kx) >> 1;
-          if (ix < 0 || ix >= p.Ws) continue;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ky = ((yy + 1) & 1) + 2 * dy, kx = ((xx + 1) & 1) + 2 * dx;
+          const int iy = (yy + 1 - ky) >> 1, ix = (xx + 1 - kx) >> 1;
+          const bool ok = iy >= 0 && iy < p.Hs && ix >= 0 && ix < p.Ws;
+          const float wgt = ok ? wy[a] * wx[b] : 0.f;
+          const int cy = min(max(iy, 0), p.Hs - 1), cx = min(max(ix, 0), p.Ws - 1);
           float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xr + ((size_t)iy * p.Ws + ix) * p.Cin)), f);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xr + ((size_t)cy * p.Ws + cx) * p.Cin)), f);
           const float* wk = s_w + (size_t)(ky * 4 + kx) * p.Cout * p.Cin + (sub << 3);
           for (int co = 0; co < p.Cout; ++co) {
-            float d = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d = fmaf(f[j], wk[co * p.Cin + j], d);
+            const float4 w0 = *reinterpret_cast<const float4*>(wk + co * p.Cin);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + co * p.Cin + 4);
+            float d = f[0] * w0.x;
+            d = fmaf(f[1], w0.y, d); d = fmaf(f[2], w0.z, d); d = fmaf(f[3], w0.w, d);
+            d = fmaf(f[4], w1.x, d); d = fmaf(f[5], w1.y, d); d = fmaf(f[6], w1.z, d); d = fmaf(f[7], w1.w, d);
             acc[co] = fmaf(wgt, d, acc[co]);
           }
         }
-      }
     }
   for (int co = 0; co < p.Cout; ++co) {
     float v = acc[co];
@@ -244,70 +387,84 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) time_tables_kernel(const TimeParams p) {
-  __shared__ float s_emb[256], s_h[512], s_t[512];
-  const TimeLayer L = p.layers[blockIdx.x];
-  const int r = blockIdx.y;
+// Stage 1: one block per distinct time value: sinusoidal embedding -> Linear -> GELU -> Linear -> SiLU, kept in global
+// memory ([tab_rows, time_dim]); the SiLU belongs to every per-block time MLP (SiLU -> Linear) and is hoisted here.
+__global__ void __launch_bounds__(256) time_embed_kernel(const TimeParams p) {
+  __shared__ float s_emb[256], s_h[512];
+  const int r = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const bool timed = p.time != nullptr && L.w_off >= 0;
-  if (timed) {
-    const float t = p.time[r];
-    const int half = p.dim / 2;
-    const float k = -logf(10000.f) / (float)(half - 1);
-    for (int i = threadIdx.x; i < half; i += blockDim.x) {
-      const float a = t * expf((float)i * k);
-      s_emb[i] = sinf(a);
-      s_emb[half + i] = cosf(a);
-    }
-    __syncthreads();
-    for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(dim, time_dim) + exact GELU
-      const float* w = p.packed + p.w1_off + (size_t)o * p.dim;
-      float s = 0.f;
-      for (int i = lane; i < p.dim; i += 32) s = fmaf(w[i], s_emb[i], s);
-      s = warp_sum(s);
-      if (lane == 0) {
-        const float v = s + p.packed[p.b1_off + o];
-        s_h[o] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-      }
-    }
-    __syncthreads();
-    for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(time_dim, time_dim), then the per-block SiLU
-      const float* w = p.packed + p.w2_off + (size_t)o * p.time_dim;
-      float s = 0.f;
-      for (int i = lane; i < p.time_dim; i += 32) s = fmaf(w[i], s_h[i], s);
-      s = warp_sum(s);
-      if (lane == 0) {
-        const float v = s + p.packed[p.b2_off + o];
-        s_t[o] = v / (1.f + expf(-v));
-      }
-    }
-    __syncthreads();
+  const float t = p.time[r];
+  const int half = p.dim / 2;
+  const double k = -log(10000.0) / (double)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = (float)exp((double)i * k);   // frequencies in fp32 like the reference (misc.py:27-28)
+    const double a = (double)(t * f);            // fp32 product, then an accurately reduced sin / cos
+    s_emb[i] = (float)sin(a);
+    s_emb[half + i] = (float)cos(a);
   }
-  float* A = p.tabA + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
-  float* B = p.tabB + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
-  for (int c = warp; c < L.C; c += nwarp) {
-    float scale = 0.f, shift = 0.f;
-    if (timed) {
-      const float* ws = p.packed + L.w_off + (size_t)c * p.time_dim;
-      const float* wh = p.packed + L.w_off + (size_t)(L.C + c) * p.time_dim;
-      float s1 = 0.f, s2 = 0.f;
-      for (int i = lane; i < p.time_dim; i += 32) {
-        s1 = fmaf(ws[i], s_t[i], s1);
-        s2 = fmaf(wh[i], s_t[i], s2);
-      }
-      scale = warp_sum(s1) + p.packed[L.b_off + c];
-      shift = warp_sum(s2) + p.packed[L.b_off + L.C + c];
-    }
+  __syncthreads();
+  for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(dim, time_dim) + exact GELU
+    const float* w = p.packed + p.w1_off + (size_t)o * p.dim;
+    float s = 0.f;
+    for (int i = lane; i < p.dim; i += 32) s = fmaf(w[i], s_emb[i], s);
+    s = warp_sum(s);
     if (lane == 0) {
-      if (L.mode == 1) {
-        A[c] = scale + 1.f;
-        B[c] = shift;
-      } else {
-        const float na = L.na_off >= 0 ? p.packed[L.na_off + c] : 1.f;
-        const float nb = L.nb_off >= 0 ? p.packed[L.nb_off + c] : 0.f;
-        A[c] = na * (scale + 1.f);
-        B[c] = nb * (scale + 1.f) + shift;
-      }
+      const float v = s + p.packed[p.b1_off + o];
+      s_h[o] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    }
+  }
+  __syncthreads();
+  for (int o = warp; o < p.time_dim; o += nwarp) {  // Linear(time_dim, time_dim), then SiLU
+    const float* w = p.packed + p.w2_off + (size_t)o * p.time_dim;
+    float s = 0.f;
+    for (int i = lane; i < p.time_dim; i += 32) s = fmaf(w[i], s_h[i], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float v = s + p.packed[p.b2_off + o];
+      p.temb[(size_t)r * p.time_dim + o] = v / (1.f + expf(-v));
+    }
+  }
+}
+
+// Stage 2: one warp per (time row, layer, channel): (scale, shift) = Linear(time_dim, 2C)(SiLU(temb)) folded with the
+// layer's norm/bias affine into the epilogue tables A, B.
+__global__ void __launch_bounds__(256) time_tables_kernel(const TimeParams p, int total_ch) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= (long long)total_ch * p.rows) return;
+  const int r = (int)(gw / total_ch);
+  const int f = (int)(gw - (long long)r * total_ch);  // flat (padded) channel index = tab_off + c
+  int li = 0;
+  for (int j = 1; j < p.n_layers; ++j)
+    if (p.layers[j].tab_off <= f) li = j;  // layers are ordered by tab_off
+  const TimeLayer L = p.layers[li];
+  const int c = f - (int)L.tab_off;
+  if (c >= L.C) return;  // padding slot
+  float scale = 0.f, shift = 0.f;
+  if (p.time != nullptr && L.w_off >= 0) {
+    const float* st = p.temb + (size_t)r * p.time_dim;
+    const float* ws = p.packed + L.w_off + (size_t)c * p.time_dim;
+    const float* wh = p.packed + L.w_off + (size_t)(L.C + c) * p.time_dim;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < p.time_dim; i += 32) {
+      const float tv = st[i];
+      s1 = fmaf(ws[i], tv, s1);
+      s2 = fmaf(wh[i], tv, s2);
+    }
+    scale = warp_sum(s1) + p.packed[L.b_off + c];
+    shift = warp_sum(s2) + p.packed[L.b_off + L.C + c];
+  }
+  if (lane == 0) {
+    float* A = p.tabA + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
+    float* B = p.tabB + (size_t)L.tab_off * p.rows + (size_t)r * L.C;
+    if (L.mode == 1) {
+      A[c] = scale + 1.f;
+      B[c] = shift;
+    } else {
+      const float na = L.na_off >= 0 ? p.packed[L.na_off + c] : 1.f;
+      const float nb = L.nb_off >= 0 ? p.packed[L.nb_off + c] : 0.f;
+      A[c] = na * (scale + 1.f);
+      B[c] = nb * (scale + 1.f) + shift;
     }
   }
 }
@@ -358,6 +515,23 @@ __global__ void __launch_bounds__(256) repack_conv_kernel(const float* __restric
   }
 }
 
+__global__ void __launch_bounds__(256) compose_conv_kernel(const float* __restrict__ w0, const float* __restrict__ wi,
+                                                          const float* __restrict__ bi, __nv_bfloat16* __restrict__ out,
+                                                          int Cm, int Cs, int taps, int Cpad, int Kpad) {
+  const int o = blockIdx.x;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    const int tap = k / Cpad, ch = k - tap * Cpad;
+    float v = 0.f;
+    if (tap < taps && ch <= Cs) {
+      for (int m = 0; m < Cm; ++m) {
+        const float a = w0[((size_t)o * Cm + m) * taps + tap];
+        v = fmaf(a, ch < Cs ? wi[(size_t)m * Cs + ch] : bi[m], v);
+      }
+    }
+    out[(size_t)o * Kpad + k] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void fold_norm_kernel(const float* bias, const float* g, const float* beta, const float* mean,
                                  const float* var, float eps, float* na, float* nb, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,8 +577,24 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
   return 0;
 }
 
+int launch_stem(const StemParams& p, cudaStream_t s) {
+  if (p.Cout != 64 || p.Cin > 16) { set_error("stem: needs dim == 64 and at most 16 input channels"); return -1; }
+  const long long total = (long long)p.pk.rows * p.pk.Ho * p.pk.Wo;
+  ProfScope prof(s, KC_PACK, 2.0 * p.Cin * 64 * (double)total, 2.0 * 64 * (double)total);
+  stem_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  DYF_LAUNCH_OK("stem_kernel");
+  return 0;
+}
+
 int launch_upsample(const UpsampleParams& p, cudaStream_t s) {
   if ((p.C[0] | p.C[1] | p.ld[0] | p.ld[1]) & 7) { set_error("upsample: channel counts must be multiples of 8"); return -1; }
+  if (p.scale == 2 && p.bilinear) {
+    const long long quads = (long long)p.rows * p.H * p.W * ((p.C[0] + p.C[1]) >> 3);
+    ProfScope prof(s, KC_UPSAMPLE, 0.0, 2.0 * 5.0 * (double)quads * 8);
+    upsample2x_quad_kernel<<<cdiv(quads, 256), 256, 0, s>>>(p);
+    DYF_LAUNCH_OK("upsample2x_quad_kernel");
+    return 0;
+  }
   const long long total = (long long)p.rows * p.H * p.scale * p.W * p.scale * ((p.C[0] + p.C[1]) >> 3);
   ProfScope prof(s, KC_UPSAMPLE, 0.0, 2.0 * 1.25 * (double)total * 8);
   upsample_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
@@ -418,15 +608,17 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
     set_error("groupnorm: unsupported channel/group configuration");
     return -1;
   }
-  DYF_CUDA_OK(cudaMemsetAsync(p.stats, 0, (size_t)p.rows * p.G * 2 * sizeof(float), s));
   const int pstep = 256 / chunks;
   int pix_per_block = pstep * 16;
-  dim3 grid(cdiv(p.HW, pix_per_block), p.rows);
+  if (cdiv(p.HW, pix_per_block) > GN_SLABS) pix_per_block = cdiv(cdiv(p.HW, GN_SLABS), pstep) * pstep;
+  GroupNormParams q = p;
+  q.slabs = cdiv(p.HW, pix_per_block);
+  dim3 grid(q.slabs, p.rows);
   ProfScope prof(s, KC_GROUPNORM);
-  groupnorm_stats_kernel<<<grid, 256, 0, s>>>(p, pix_per_block);
+  groupnorm_stats_kernel<<<grid, 256, 0, s>>>(q, pix_per_block);
   DYF_LAUNCH_OK("groupnorm_stats_kernel");
   const long long total = (long long)p.rows * p.HW * chunks;
-  groupnorm_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  groupnorm_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(q);
   DYF_LAUNCH_OK("groupnorm_apply_kernel");
   return 0;
 }
@@ -448,9 +640,13 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s) {
 int launch_time_tables(const TimeParams& p, cudaStream_t s) {
   if (p.dim > 256 || p.time_dim > 512) { set_error("time tables: dim too large"); return -1; }
   if (p.n_layers == 0) return 0;
-  dim3 grid(p.n_layers, p.rows);
   ProfScope prof(s, KC_TIME);
-  time_tables_kernel<<<grid, 128, 0, s>>>(p);
+  if (p.time != nullptr) {
+    time_embed_kernel<<<p.rows, 256, 0, s>>>(p);
+    DYF_LAUNCH_OK("time_embed_kernel");
+  }
+  const long long warps = (long long)p.total_ch * p.rows;
+  time_tables_kernel<<<cdiv(warps * 32, 256), 256, 0, s>>>(p, p.total_ch);
   DYF_LAUNCH_OK("time_tables_kernel");
   return 0;
 }
@@ -459,6 +655,13 @@ int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH,
                        int standardize, cudaStream_t s) {
   repack_conv_kernel<<<O, 256, 0, s>>>(w, out, I, KH, KW, Cpad, Kpad, standardize);
   DYF_LAUNCH_OK("repack_conv_kernel");
+  return 0;
+}
+
+int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_bfloat16* out, int O, int Cm, int Cs,
+                        int KH, int KW, int Cpad, int Kpad, cudaStream_t s) {
+  compose_conv_kernel<<<O, 256, 0, s>>>(w0, wi, bi, out, Cm, Cs, KH * KW, Cpad, Kpad);
+  DYF_LAUNCH_OK("compose_conv_kernel");
   return 0;
 }
 

@@ -13,6 +13,7 @@ struct ConvParams {
   void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32
   const float* tabA;         // [rows, Cout]  y = acc * A + B   (folded norm, conv bias, time scale/shift)
   const float* tabB;         // [rows, Cout]
+  int tab_div;               // table row of batch row r is r / tab_div (rows of one logical call share a table)
   const __nv_bfloat16* res;  // optional residual added after activation+dropout, [M, res_ld]
   int rows, Hi, Wi, Cin;
   int Cin_real;              // un-padded input channels (FLOP accounting only)
@@ -30,8 +31,8 @@ struct ConvParams {
 __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m, int c0, const float* acc) {
   const int HoWo = p.Ho * p.Wo;
   const int r = (int)(m / HoWo);
-  const float* A = p.tabA + (size_t)r * p.Cout + c0;
-  const float* B = p.tabB + (size_t)r * p.Cout + c0;
+  const float* A = p.tabA + (size_t)(r / p.tab_div) * p.Cout + c0;
+  const float* B = p.tabB + (size_t)(r / p.tab_div) * p.Cout + c0;
   float v[8];
   const bool full = (c0 + 8 <= p.Cout) && ((p.Cout & 3) == 0);
   if (full) {
@@ -90,6 +91,7 @@ int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 bool conv_umma_eligible(const ConvParams& p);
 bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad);
-int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int standardize, cudaStream_t s);
+int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
+                       cudaStream_t s);
 
 }  // namespace dyf

@@ -1,31 +1,76 @@
-// Implicit-GEMM 3x3 (stride 1) convolution on the 5th-generation tensor cores: tcgen05.mma (UMMA) with the
-// accumulator in TMEM, weights streamed by bulk-TMA (cp.async.bulk + mbarrier complete_tx) and the activations
-// staged ONCE per channel chunk as a halo patch that all nine taps re-read through shifted UMMA descriptors.
+// Implicit-GEMM convolutions on the 5th-generation tensor cores: tcgen05.mma (UMMA) with the accumulator in TMEM,
+// weights streamed by bulk-TMA (cp.async.bulk + mbarrier complete_tx) and the activations staged ONCE per channel
+// chunk as a halo patch that every filter tap re-reads through shifted UMMA shared-memory descriptors.
 //
-// Tile: 16 x 8 output pixels (M = 128) x BN output channels.  For a 64-channel chunk the input patch is
-// 18 x 10 pixels; it is stored K-major / no-swizzle as eight 16-byte channel planes [chunk8][pixel], so that
-//   * 8 consecutive M rows (one UMMA core matrix) = 8 consecutive pixels of a patch row  (16 B apart),
-//   * consecutive 8-row groups = consecutive patch rows                                   (SBO = 10 * 16 B),
-//   * the two 16-byte K halves of a K=16 step = consecutive channel planes                 (LBO = plane stride),
-// and tap (ky, kx) is nothing but a start-address offset of (ky * 10 + kx) * 16 B.  Activations therefore cross
-// L2 -> SM once (x1.4 halo) instead of nine times, which is what lets the N = 64 / 128 layers (60 % of the
-// Navier-Stokes FLOPs) feed the tensor pipe.  Zero padding = zero-filled cp.async.
+// Tile: 16 x 8 output pixels (M = 128) x BN output channels.  Two geometries share one kernel:
+//   S1K3  3x3, stride 1, pad 1 (decoder):  64-channel chunks, patch 18 x 10 pixels, 9 taps
+//   S2K4  4x4, stride 2, pad 1 (encoder):  32-channel chunks, patch 34 x 18 pixels split by column parity, 16 taps
+// A patch is stored K-major / no-swizzle as 16-byte channel planes [plane][pixel], so that
+//   * 8 consecutive M rows (one UMMA core matrix) = 8 consecutive pixels of a patch row        (16 B apart),
+//   * consecutive 8-row groups = consecutive (S1) / every other (S2) patch row                 (SBO),
+//   * the two 16-byte K halves of a K=16 step = consecutive channel planes                     (LBO = plane stride),
+// and a tap (ky, kx) is nothing but a start-address offset.  For stride 2 the patch columns are de-interleaved by
+// parity while they are gathered, which turns the stride-2 pixel walk of a tap into a unit-stride one.
+// Activations therefore cross L2 -> SM once (x1.4 halo for 3x3) instead of once per tap, which is what lets the
+// N = 64 / 128 layers (most of the Navier-Stokes FLOPs) feed the tensor pipe.  Zero padding = zero-filled cp.async.
 //
-// Warp roles (192 threads): warps 0-3 gather patches (cp.async) and later run the epilogue (tcgen05.ld ->
-// fused affine/activation/dropout -> 128-bit stores), warp 4 allocates TMEM and issues the MMAs (one thread),
-// warp 5 streams weight tiles.  Pipelines: A patches 2 stages, B tiles 4 stages, all on mbarriers.
+// Persistent, warp-specialised CTA (448 threads, one per SM): warps 0-7 run the epilogue (tcgen05.ld -> fused affine /
+// activation / dropout / residual -> 128-bit stores), warps 8-11 gather patches (cp.async, completion signalled
+// straight to an mbarrier), warp 12 owns TMEM and issues the MMAs (one thread), warp 13 streams weight tiles.
+// Two TMEM accumulators ping-pong, so the epilogue of tile i overlaps the MMAs of tile i+1 and the A/B rings
+// (3-4 patch stages, 6-8 weight stages, all on mbarriers) keep streaming across tile boundaries.
 #include "conv.cuh"
 
 namespace dyf {
 namespace {
 
-constexpr int TILE_H = 16, TILE_W = 8;          // output pixels per CTA tile (M = 128)
-constexpr int PATCH_H = TILE_H + 2, PATCH_W = TILE_W + 2;
-constexpr int PATCH_PIX = PATCH_H * PATCH_W;    // 180
-constexpr int A_PLANE = (PATCH_PIX + 1) * 16;   // bytes per 8-channel plane; odd pixel pitch => conflict-free fills
-constexpr int A_STAGE = 8 * A_PLANE;            // one 64-channel chunk
-constexpr int A_STAGES = 2, B_STAGES = 3;
-constexpr int THREADS = 192;
+constexpr int TILE_H = 16, TILE_W = 8;  // output pixels per CTA tile (M = 128)
+constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each draining half of the accumulator columns
+constexpr int THREADS = (EPI_WARPS + 4 + 2) * 32;  // epilogue + 4 producer warps + MMA warp + weight-stream warp
+
+enum Mode { S1K3 = 0, S2K4 = 1 };
+
+template <int MODE> struct Geo;
+template <> struct Geo<S1K3> {
+  static constexpr int CH = 64;                     // channels per chunk
+  static constexpr int PLANES = 8;                  // 16-byte planes per chunk
+  static constexpr int CPL = 8;                     // 8-channel groups per pixel in a chunk
+  static constexpr int PH = TILE_H + 2, PW = TILE_W + 2;
+  static constexpr int PIX = PH * PW;               // gathered pixels
+  static constexpr int SLOTS = PIX;                 // pixel slots per plane
+  static constexpr int TAPS = 9, KW = 3;
+  static constexpr int GT = 3;                      // taps per weight stage (one filter row)
+  static constexpr int SBO = PW * 16;
+  __device__ static int tap_offset(int ky, int kx, int /*plane_bytes*/) { return (ky * PW + kx) * 16; }
+  __device__ static int slot(int pr, int pc) { return pr * PW + pc; }
+  __device__ static int plane_of(int g, int /*pc*/) { return g; }
+  __device__ static int in_y(int oy0, int pr) { return oy0 - 1 + pr; }
+  __device__ static int in_x(int ox0, int pc) { return ox0 - 1 + pc; }
+};
+template <> struct Geo<S2K4> {
+  static constexpr int CH = 32;
+  static constexpr int PLANES = 8;                  // 2 column parities x 4 channel groups
+  static constexpr int CPL = 4;
+  static constexpr int PH = 2 * TILE_H + 2, PW = 2 * TILE_W + 2, PWH = PW / 2;
+  static constexpr int PIX = PH * PW;
+  static constexpr int SLOTS = PH * PWH;
+  static constexpr int TAPS = 16, KW = 4;
+  static constexpr int GT = 4;
+  static constexpr int SBO = 2 * PWH * 16;          // output row r reads patch row 2r + ky
+  __device__ static int tap_offset(int ky, int kx, int plane_bytes) {
+    return (kx & 1) * CPL * plane_bytes + (ky * PWH + (kx >> 1)) * 16;
+  }
+  __device__ static int slot(int pr, int pc) { return pr * PWH + (pc >> 1); }
+  __device__ static int plane_of(int g, int pc) { return (pc & 1) * CPL + g; }
+  __device__ static int in_y(int oy0, int pr) { return 2 * oy0 - 1 + pr; }
+  __device__ static int in_x(int ox0, int pc) { return 2 * ox0 - 1 + pc; }
+};
+template <int MODE> struct Sizes {
+  using G = Geo<MODE>;
+  static constexpr int PLANE = (G::SLOTS | 1) * 16;  // odd slot pitch => conflict-free 16-byte fills across planes
+  static constexpr int A_STAGE = G::PLANES * PLANE;
+  static constexpr int KSTEPS = G::CH / 16;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,10 +100,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int by
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {  // arrive when this thread's prior cp.async land
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -89,117 +130,95 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
+template <int AS, int BS>
 struct __align__(8) Barriers {
-  uint64_t a_full[A_STAGES], a_empty[A_STAGES], b_full[B_STAGES], b_empty[B_STAGES], acc_full;
+  uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
-                                                              int tiles_x, int tiles_y) {
+// Persistent kernel: one CTA per SM walks the work list (n_tile fastest, so CTAs sharing an activation tile run
+// together and hit it in L2).  All pipelines run across tile boundaries: the A/B rings keep streaming into the next
+// tile while the epilogue warps drain the previous accumulator (two TMEM accumulators, ping-pong).
+template <int BN, int MODE, int AS, int BS>
+__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
+                                                              int tiles_x, int tiles_y, int n_tiles, int num_work) {
+  using G = Geo<MODE>;
+  using S = Sizes<MODE>;
+  constexpr int PLANE = S::PLANE, A_STAGE = S::A_STAGE, KSTEPS = S::KSTEPS;
+  constexpr int B_TAP = BN * G::CH * 2;    // one tap of one chunk: [k8][BN rows][16 B]
+  constexpr int B_STAGE = G::GT * B_TAP;   // a weight stage carries one filter row (GT taps)
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int B_STAGE = BN * 128;  // [kchunk 8][BN rows][16 B]
   uint8_t* sA = smem;
-  uint8_t* sB = smem + A_STAGES * A_STAGE;
-  Barriers* bars = reinterpret_cast<Barriers*>(sB + B_STAGES * B_STAGE);
-  float* s_tab = reinterpret_cast<float*>(bars + 1);  // [2][BN]: epilogue multiplier / offset of this (row, n_tile)
+  uint8_t* sB = smem + AS * A_STAGE;
+  using Bars = Barriers<AS, BS>;
+  Bars* bars = reinterpret_cast<Bars*>(sB + BS * B_STAGE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tile = blockIdx.y;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int row = t / tiles_y;           // batch row
-  const int oy0 = ty * TILE_H, ox0 = tx * TILE_W;
-  const int nchunks = p.Cin >> 6;        // 64-channel chunks
+  const int nchunks = p.Cin / G::CH;
+  const int tiles_per_row = tiles_x * tiles_y;
 
   if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-    mbar_init(smem_u32(&bars->acc_full), 1);
+    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // TMEM allocation (power of two >= 32 columns), owned by this warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(BN));
+  if (warp == EPI_WARPS + 4) {  // TMEM: two accumulators of BN fp32 columns, owned by the MMA warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  if (warp == 5) {  // per-(row, channel) epilogue tables: one batch row per tile, so a plain smem copy suffices
-    const size_t tb = (size_t)row * p.Cout + n_tile * BN;
-    for (int i = lane; i < BN; i += 32) { s_tab[i] = __ldg(p.tabA + tb + i); s_tab[BN + i] = __ldg(p.tabB + tb + i); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = bars->tmem_base;
+  const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp < 4) {
-    // =============================== A producer: halo patches via cp.async (zero fill = padding) ===============
-    constexpr int ITEMS = PATCH_PIX * 8;               // 16-byte items per chunk
-    constexpr int ITERS = (ITEMS + 127) / 128;
-    const int chunk8 = tid & 7;                        // fixed 8-channel plane of this thread (128 % 8 == 0)
-    int src_off[ITERS];                                // element offset of the patch pixel, -1 = outside the image
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int pix = (tid >> 3) + it * 16;
-      int off = -1;
-      if (pix < PATCH_PIX) {
-        const int pr = pix / PATCH_W, pc = pix - pr * PATCH_W;
-        const int iy = oy0 - 1 + pr, ix = ox0 - 1 + pc;
-        if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi) off = (iy * p.Wi + ix) * p.Cin;
-      }
-      src_off[it] = off;
-    }
-    const __nv_bfloat16* in_row = p.in + (size_t)row * p.Hi * p.Wi * p.Cin + chunk8 * 8;
-    const __nv_bfloat16* const in_base = p.in;
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c % A_STAGES;
-      mbar_wait(smem_u32(&bars->a_empty[st]), ((c / A_STAGES) & 1) ^ 1);
-      const uint32_t dst0 = smem_u32(sA + st * A_STAGE + chunk8 * A_PLANE);
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int pix = (tid >> 3) + it * 16;
-        if (pix < PATCH_PIX) {
-          const bool v = src_off[it] >= 0;
-          cp_async16(dst0 + pix * 16, v ? (const void*)(in_row + src_off[it] + c * 64) : (const void*)in_base, v ? 16 : 0);
-        }
-      }
-      // hardware arrives on a_full[st] once this thread's copies have landed (no wait, no proxy fence needed:
-      // same pattern as CUTLASS's sm100 cp.async mainloop); the producer immediately moves on to the next chunk
-      cp_async_arrive_noinc(smem_u32(&bars->a_full[st]));
-    }
+  // work item -> (n_tile, batch row, tile origin)
+  auto decode = [&](int w, int& n_tile, int& row, int& oy0, int& ox0) {
+    n_tile = w % n_tiles;
+    int t = w / n_tiles;
+    row = t / tiles_per_row;
+    t -= row * tiles_per_row;
+    const int ty = t / tiles_x;
+    oy0 = ty * TILE_H;
+    ox0 = (t - ty * tiles_x) * TILE_W;
+  };
 
-    // =============================== epilogue: TMEM -> registers -> fused math -> global ===========================
-    mbar_wait(smem_u32(&bars->acc_full), 0);
-    tc_fence_after();
-    const int m_local = warp * 32 + lane;               // accumulator row = TMEM lane
-    const int oy = oy0 + (m_local >> 3), ox = ox0 + (m_local & 7);
-    const bool valid = oy < p.Ho && ox < p.Wo;
-    const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
-    __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
-    const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+  if (warp < EPI_WARPS) {
+    // =============================== epilogue warps: TMEM -> registers -> fused math -> global ====================
     const int act = p.act;
     const uint32_t thresh = p.drop.thresh;
     const float dscale = p.drop.scale;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      int n_tile, row, oy0, ox0;
+      decode(w, n_tile, row, oy0, ox0);
+      const int acc = it & 1;
+      const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
+      const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
+      const int oy = oy0 + (m_local >> 3), ox = ox0 + (m_local & 7);
+      const bool valid = oy < p.Ho && ox < p.Wo;
+      const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
+      __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
+      const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+      const float* const tA = p.tabA + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
+      const float* const tB = p.tabB + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
+      mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      constexpr int COLS = BN / (EPI_WARPS / 4);  // columns drained by this warp
+      const int cbeg = (warp >> 2) * COLS;
 #pragma unroll 2
-    for (int c0 = 0; c0 < BN; c0 += 8) {
-      {
+      for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
         uint32_t v[8];
-        tmem_ld8(tmem_acc + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld8(taddr + c0, v);
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(tA + c0)), a1 = __ldg(reinterpret_cast<const float4*>(tA + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(tB + c0)), b1 = __ldg(reinterpret_cast<const float4*>(tB + c0 + 4));
         float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaf(__uint_as_float(v[j]), s_tab[c0 + j], s_tab[BN + c0 + j]);
+        y[0] = fmaf(__uint_as_float(v[0]), a0.x, b0.x); y[1] = fmaf(__uint_as_float(v[1]), a0.y, b0.y);
+        y[2] = fmaf(__uint_as_float(v[2]), a0.z, b0.z); y[3] = fmaf(__uint_as_float(v[3]), a0.w, b0.w);
+        y[4] = fmaf(__uint_as_float(v[4]), a1.x, b1.x); y[5] = fmaf(__uint_as_float(v[5]), a1.y, b1.y);
+        y[6] = fmaf(__uint_as_float(v[6]), a1.z, b1.z); y[7] = fmaf(__uint_as_float(v[7]), a1.w, b1.w);
         switch (act) {
           case ACT_RELU:
 #pragma unroll
@@ -234,101 +253,189 @@ __global__ void __launch_bounds__(THREADS) conv3x3_umma_kernel(const ConvParams 
           *reinterpret_cast<uint4*>(orow + c0) = pack8(y);
         }
       }
+      tc_fence_before();                                    // all tcgen05.ld of this accumulator have completed
+      mbar_arrive(smem_u32(&bars->acc_empty[acc]));         // hand the accumulator back to the MMA warp
     }
-  } else if (warp == 4) {
+  } else if (warp < EPI_WARPS + 4) {
+    // =============================== A producers: halo patches via cp.async (zero fill = padding) ================
+    const int ptid = tid - EPI_WARPS * 32;
+    constexpr int PSTEP = 128 / G::CPL;                     // patch pixels covered per pass of the 128 threads
+    constexpr int ITERS = (G::PIX + PSTEP - 1) / PSTEP;
+    const int g8 = ptid % G::CPL;                           // fixed 8-channel group of this thread
+    const __nv_bfloat16* const in_base = p.in;
+    int ca = 0;                                             // running chunk counter (A ring position)
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      int n_tile, row, oy0, ox0;
+      decode(w, n_tile, row, oy0, ox0);
+      int src_off[ITERS];                                   // element offset of the patch pixel, -1 = outside the image
+      int dst_off[ITERS];                                   // byte offset inside a stage, -1 = no such pixel
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int pix = ptid / G::CPL + it * PSTEP;
+        int so = -1, dof = -1;
+        if (pix < G::PIX) {
+          const int pr = pix / G::PW, pc = pix - pr * G::PW;
+          const int iy = G::in_y(oy0, pr), ix = G::in_x(ox0, pc);
+          if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi) so = (iy * p.Wi + ix) * p.Cin;
+          dof = G::plane_of(g8, pc) * PLANE + G::slot(pr, pc) * 16;
+        }
+        src_off[it] = so;
+        dst_off[it] = dof;
+      }
+      const __nv_bfloat16* const in_row = in_base + (size_t)row * p.Hi * p.Wi * p.Cin + g8 * 8;
+      for (int c = 0; c < nchunks; ++c, ++ca) {
+        const int st = ca % AS;
+        mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
+        const uint32_t dst0 = smem_u32(sA + st * A_STAGE);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          if (dst_off[it] >= 0) {
+            const bool v = src_off[it] >= 0;
+            cp_async16(dst0 + dst_off[it], v ? (const void*)(in_row + src_off[it] + c * G::CH) : (const void*)in_base,
+                       v ? 16 : 0);
+          }
+        }
+        // hardware arrives on a_full[st] once this thread's copies have landed (no wait, no proxy fence: the same
+        // pattern as CUTLASS's sm100 cp.async mainloop); the producer immediately moves on to the next chunk
+        cp_async_arrive_noinc(smem_u32(&bars->a_full[st]));
+      }
+    }
+  } else if (warp == EPI_WARPS + 4) {
     // =============================== MMA issuer (one elected thread) ==============================================
+    // The issue loop is latency-critical (one thread feeds the whole tensor pipe): descriptors are advanced by adding
+    // compile-time constants to pre-built low words, taps are fully unrolled, and barriers are touched once per
+    // filter row (GT taps x KSTEPS MMAs) rather than once per tap.
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      int ib = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % A_STAGES;
-        mbar_wait(smem_u32(&bars->a_full[st]), (c / A_STAGES) & 1);
+      const uint32_t a_hi = (uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14);          // SBO | version 1 (bit 46)
+      const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
+      const uint32_t a_lo0 = ((uint32_t)(PLANE >> 4) << 16) | (smem_u32(sA) >> 4);      // LBO | start address
+      const uint32_t b_lo0 = ((uint32_t)((BN * 16) >> 4) << 16) | (smem_u32(sB) >> 4);
+      const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
+      const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;  // ring positions / phase parities
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + st * A_STAGE);
-        for (int tap = 0; tap < 9; ++tap, ++ib) {
-          const int sb = ib % B_STAGES;
-          mbar_wait(smem_u32(&bars->b_full[sb]), (ib / B_STAGES) & 1);
+        const uint32_t tmem_acc = tmem_base + acc * BN;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar_a_full + sa * 8, pa);
           tc_fence_after();
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const uint32_t a_tap = a_base + (ky * PATCH_W + kx) * 16;
-          const uint32_t b_base = smem_u32(sB + sb * B_STAGE);
+          const uint32_t a_lo = a_lo0 + sa * (A_STAGE >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {  // 64 channels = 4 x (K = 16)
-            const uint64_t ad = smem_desc(a_tap + ks * 2 * A_PLANE, A_PLANE, PATCH_W * 16);
-            const uint64_t bd = smem_desc(b_base + ks * 2 * (BN * 16), BN * 16, 128);
-            umma_bf16(tmem_acc, ad, bd, idesc, (c | tap | ks) != 0);
+          for (int g = 0; g < G::TAPS / G::GT; ++g) {
+            mbar_wait(bar_b_full + sb * 8, pb);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + sb * (B_STAGE >> 4);
+#pragma unroll
+            for (int t = 0; t < G::GT; ++t) {
+              const int tap = g * G::GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS; ++ks) {  // one chunk = KSTEPS x (K = 16)
+                const uint32_t alo = a_lo + ((G::tap_offset(ky, kx, PLANE) + ks * 2 * PLANE) >> 4);
+                const uint32_t blo = b_lo + ((t * B_TAP + ks * 2 * (BN * 16)) >> 4);
+                const uint64_t ad = ((uint64_t)a_hi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
+                umma_bf16(tmem_acc, ad, bd, idesc, (tap | ks) ? 1u : (uint32_t)(c != 0));
+              }
+            }
+            umma_commit(bar_b_empty + sb * 8);  // weight stage free once these MMAs retire
+            if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          umma_commit(smem_u32(&bars->b_empty[sb]));   // weight stage free once these MMAs retire
+          umma_commit(bar_a_empty + sa * 8);    // patch stage free
+          if (++sa == AS) { sa = 0; pa ^= 1; }
         }
-        umma_commit(smem_u32(&bars->a_empty[st]));     // patch stage free
+        umma_commit(smem_u32(&bars->acc_full[acc]));  // accumulator complete -> epilogue
       }
-      umma_commit(smem_u32(&bars->acc_full));          // accumulator complete -> epilogue
     }
   } else {
     // =============================== B producer: bulk-TMA weight tiles =============================================
     if (lane == 0) {
-      const int total = nchunks * 9;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(wblob) + (size_t)n_tile * total * B_STAGE;
-      for (int ib = 0; ib < total; ++ib) {
-        const int sb = ib % B_STAGES;
-        mbar_wait(smem_u32(&bars->b_empty[sb]), ((ib / B_STAGES) & 1) ^ 1);
-        mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_STAGE);
-        bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)ib * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
+      const int per_tile = nchunks * (G::TAPS / G::GT);
+      int sb = 0, pb = 1;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int n_tile = w % n_tiles;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wblob) + (size_t)n_tile * per_tile * B_STAGE;
+        for (int i = 0; i < per_tile; ++i) {
+          mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
+          mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_STAGE);
+          bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
+          if (++sb == BS) { sb = 0; pb ^= 1; }
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(BN));
+  if (warp == EPI_WARPS + 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
   }
 }
 
-// weights fp32 [O, I, 3, 3] -> bf16 blobs [n_tile][chunk][tap][k8 (8)][n (BN)][8]  (one contiguous tile per MMA stage)
+// weights fp32 [O, I, KH, KW] -> bf16 stage tiles [n_tile][chunk][tap][k8][n (BN)][8]: one contiguous blob per MMA stage
 __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                         int O, int I, int BN, int standardize) {
-  const int nchunks = I >> 6;
-  const long long total = (long long)O * I * 9;
+                                                         int O, int I, int BN, int taps, int ch, int standardize) {
+  const int nchunks = I / ch, k8n = ch / 8;
+  const long long total = (long long)O * I * taps;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  // decode the destination index
   long long r = idx;
   const int e = (int)(r % 8); r /= 8;
   const int n = (int)(r % BN); r /= BN;
-  const int k8 = (int)(r % 8); r /= 8;
-  const int tap = (int)(r % 9); r /= 9;
+  const int k8 = (int)(r % k8n); r /= k8n;
+  const int tap = (int)(r % taps); r /= taps;
   const int chunk = (int)(r % nchunks); r /= nchunks;
   const int n_tile = (int)r;
-  const int o = n_tile * BN + n, ci = chunk * 64 + k8 * 8 + e;
-  float v = w[((size_t)o * I + ci) * 9 + tap];
+  const int o = n_tile * BN + n, ci = chunk * ch + k8 * 8 + e;
+  float v = w[((size_t)o * I + ci) * taps + tap];
   if (standardize) {  // WeightStandardizedConv2d (reference unet.py:32-40), recomputed per element (load-time only)
-    const float* wo = w + (size_t)o * I * 9;
+    const float* wo = w + (size_t)o * I * taps;
     float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < I * 9; ++i) s1 += wo[i];
-    const float mean = s1 / (I * 9);
-    for (int i = 0; i < I * 9; ++i) { const float d = wo[i] - mean; s2 += d * d; }
-    v = (v - mean) * rsqrtf(s2 / (I * 9) + 1e-5f);
+    for (int i = 0; i < I * taps; ++i) s1 += wo[i];
+    const float mean = s1 / (I * taps);
+    for (int i = 0; i < I * taps; ++i) { const float d = wo[i] - mean; s2 += d * d; }
+    v = (v - mean) * rsqrtf(s2 / (I * taps) + 1e-5f);
   }
   out[idx] = __float2bfloat16_rn(v);
 }
 
-template <int BN>
+template <int MODE, int BN> struct Stages;  // pipeline depths that fill the 227 KB of one SM
+template <> struct Stages<S1K3, 64> { static constexpr int A = 3, B = 4; };   //  70 KB patches +  96 KB weights
+template <> struct Stages<S1K3, 128> { static constexpr int A = 3, B = 3; };  //  70 KB patches + 144 KB weights
+template <> struct Stages<S2K4, 64> { static constexpr int A = 3, B = 4; };   // 118 KB patches +  64 KB weights
+template <> struct Stages<S2K4, 128> { static constexpr int A = 3, B = 3; };  // 118 KB patches +  96 KB weights
+
+template <int BN, int MODE>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  constexpr int smem = A_STAGES * A_STAGE + B_STAGES * BN * 128 + (int)sizeof(Barriers) + 2 * BN * 4 + 64;
-  static bool configured = false;
-  if (!configured) {
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv3x3_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+  using G = Geo<MODE>;
+  constexpr int AS = Stages<MODE, BN>::A, BS = Stages<MODE, BN>::B;
+  constexpr int smem = AS * Sizes<MODE>::A_STAGE + BS * G::GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DYF_CUDA_OK(cudaGetDevice(&dev));
+    DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W, tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
-  dim3 grid((unsigned)(tiles_x * tiles_y * p.rows), (unsigned)(p.Cout / BN));
-  const double flops = 2.0 * (double)p.M * p.Cout * 9.0 * p.Cin_real;
+  const int n_tiles = p.Cout / BN;
+  const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
+  if (work > 0x7fffffffLL) { set_error("conv_umma: too many tiles"); return -1; }
+  const int grid = (int)(work < num_sms ? work : num_sms);
+  const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv3x3_umma_kernel<BN><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y);
-  DYF_LAUNCH_OK("conv3x3_umma_kernel");
+  conv_umma_kernel<BN, MODE, AS, BS><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work);
+  DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
+}
+
+int mode_of(int k, int stride, int pad) {
+  if (k == 3 && stride == 1 && pad == 1) return S1K3;
+  if (k == 4 && stride == 2 && pad == 1) return S2K4;
+  return -1;
 }
 
 }  // namespace
@@ -336,22 +443,30 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
 int umma_tile_n(int Cout) { return Cout == 64 ? 64 : 128; }
 
 bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad) {
-  return k == 3 && stride == 1 && pad == 1 && Cin_pad % 64 == 0 && (Cout == 64 || Cout % 128 == 0);
+  const int mode = mode_of(k, stride, pad);
+  if (mode < 0 || !(Cout == 64 || Cout % 128 == 0)) return false;
+  return Cin_pad % (mode == S1K3 ? 64 : 32) == 0;
 }
 
 bool conv_umma_eligible(const ConvParams& p) {
-  return p.w_umma != nullptr && conv_umma_shape_ok(p.Cin, p.Cout, p.KH, p.stride, p.pad) && p.KW == 3 &&
-         p.Ho == p.Hi && p.Wo == p.Wi && p.out_fp32 != 2;
+  return p.w_umma != nullptr && p.KH == p.KW && conv_umma_shape_ok(p.Cin, p.Cout, p.KH, p.stride, p.pad) &&
+         p.out_fp32 == 0 && ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
 }
 
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
-  return umma_tile_n(p.Cout) == 64 ? launch_t<64>(p, stream) : launch_t<128>(p, stream);
+  const bool n64 = umma_tile_n(p.Cout) == 64;
+  if (mode_of(p.KH, p.stride, p.pad) == S1K3) return n64 ? launch_t<64, S1K3>(p, stream) : launch_t<128, S1K3>(p, stream);
+  return n64 ? launch_t<64, S2K4>(p, stream) : launch_t<128, S2K4>(p, stream);
 }
 
-int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int standardize, cudaStream_t s) {
-  const long long total = (long long)O * I * 9;
-  repack_umma_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, O, I, umma_tile_n(O), standardize);
+int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
+                       cudaStream_t s) {
+  const int mode = mode_of(k, stride, pad);
+  if (mode < 0) { set_error("repack_umma: unsupported geometry"); return -1; }
+  const int taps = k * k, ch = mode == S1K3 ? 64 : 32;
+  const long long total = (long long)O * I * taps;
+  repack_umma_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, O, I, umma_tile_n(O), taps, ch, standardize);
   DYF_LAUNCH_OK("repack_umma_kernel");
   return 0;
 }

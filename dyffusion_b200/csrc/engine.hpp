@@ -28,6 +28,7 @@ struct ConvLayer {
   bool standardize = false;                   // WeightStandardizedConv2d
   int K = 0, Kpad = 0;
   size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
+  int comp_wi = -1, comp_bi = -1, comp_cm = 0;  // composite layer: preceded by a folded 1x1 conv (weights, bias, width)
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
   int table = -1;                             // index into Net::time_layers
@@ -40,7 +41,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
 constexpr int BUF_NONE = -1;
 
 struct Op {
@@ -53,6 +54,7 @@ struct Op {
   int out_coff = 0;    // channel offset inside the output buffer (concat writes)
   int out_mode = 0;    // 0 bf16 NHWC buffer, 2 fp32 NCHW external output
   int c0 = 0, c1 = 0, scale = 2, bilinear = 1;  // upsample
+  int ones_channel = -1;  // pack: channel carrying a folded bias
   int aux = 0;
 };
 
@@ -99,7 +101,7 @@ struct Net {
   size_t workspace_bytes(int rows) const;
   int forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
               const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s,
-              int noise_src = -1, float noise_w = 0.f, int src_rows = 0);
+              int noise_src = -1, float noise_w = 0.f, int src_rows = 0, int group_rows = 1);
 };
 
 struct Sampler {

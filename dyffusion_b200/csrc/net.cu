@@ -56,7 +56,7 @@ int Net::add_conv(const std::string& prefix, int Cin, int Cout, int k, int strid
   wq_elems += (size_t)Cout * c.Kpad;
   if (conv_umma_shape_ok(c.Cpad, Cout, k, stride, pad) && c.Cpad == Cin) {
     c.wu_off = (long long)wu_elems;
-    wu_elems += (size_t)Cout * Cin * 9;
+    wu_elems += (size_t)Cout * Cin * k * k;
   }
   c.na_off = packed_floats + extra_floats;  // resolved against the final packed size in finalize()
   extra_floats += round_up(Cout, 4);
@@ -124,7 +124,7 @@ int Net::build() {
   stats_floats_per_row = 0;
   for (auto& n : norms) {
     n.stats_off = stats_floats_per_row;
-    stats_floats_per_row += 2 * n.G;
+    stats_floats_per_row += 2 * n.G * 32;
     if (n.tw >= 0) {
       TimeLayer L{};
       L.w_off = params[n.tw].off;
@@ -157,12 +157,33 @@ int Net::build_unet_simple() {
   if (dim % 8) { set_error("unet_simple: dim must be a multiple of 8"); return DYF_ERR_UNSUPPORTED; }
   int site = 1;
   // stem: [resize ->] 1x1 conv (:113-116)
-  const int b_in = add_buf(Hin, Win, round_up(cin, 8));
-  Op pk{}; pk.type = OP_PACK; pk.out = b_in; pk.bilinear = resize ? 1 : 0;
-  ops.push_back(pk);
-  int ci = add_conv("init_conv", cin, dim, 1, 1, 0);
-  int x = add_buf(Hin, Win, dim);
-  { Op o{}; o.type = OP_CONV; o.in0 = b_in; o.out = x; o.layer = ci; o.act = ACT_NONE; o.drop_p = d.input_dropout; o.site = site++; ops.push_back(o); }
+  // The stem is linear (1x1 conv, no activation): with input_dropout == 0 it is folded into the first encoder conv
+  // as a composite 4x4/s2 conv over the C_in resized input channels plus a "ones" channel that carries the stem bias
+  // (zero in the padding, exactly like the padded stem output).  The 64-channel full-resolution stem output -- the
+  // largest activation of the encoder -- is then never materialised.  Exact in real arithmetic.
+  const bool fold_stem = d.input_dropout == 0.f;
+  int x = BUF_NONE;
+  int stem_w = -1, stem_b = -1, b_in = BUF_NONE;
+  if (fold_stem) {
+    stem_w = add_param("init_conv.weight", {dim, cin, 1, 1});
+    stem_b = add_param("init_conv.bias", {dim});
+    b_in = add_buf(Hin, Win, round_up(cin + 1, 8));
+    Op pk{}; pk.type = OP_PACK; pk.out = b_in; pk.bilinear = resize ? 1 : 0; pk.ones_channel = cin;
+    ops.push_back(pk);
+  } else {
+    int ci = add_conv("init_conv", cin, dim, 1, 1, 0);
+    x = add_buf(Hin, Win, dim);
+    if (dim == 64 && cin <= 16) {  // fused resize + 1x1 conv: the resized input is never materialised
+      Op o{}; o.type = OP_STEM; o.out = x; o.layer = ci; o.bilinear = resize ? 1 : 0; o.drop_p = d.input_dropout; o.site = site++;
+      ops.push_back(o);
+    } else {
+      const int bi = add_buf(Hin, Win, round_up(cin, 8));
+      Op pk{}; pk.type = OP_PACK; pk.out = bi; pk.bilinear = resize ? 1 : 0;
+      ops.push_back(pk);
+      Op o{}; o.type = OP_CONV; o.in0 = bi; o.out = x; o.layer = ci; o.act = ACT_NONE; o.drop_p = d.input_dropout; o.site = site++;
+      ops.push_back(o);
+    }
+  }
   // encoder (:120-129): conv(k, s2) -> BN|GN -> time scale/shift -> LeakyReLU(0.2) -> Dropout
   const int enc_out[6] = {dim * 2, dim * 2, dim * 4, dim * 8, dim * 8, dim * 8};
   const int enc_k[6] = {4, 4, 4, 4, 2, 2}, enc_p[6] = {1, 1, 1, 1, 0, 0};
@@ -173,6 +194,14 @@ int Net::build_unet_simple() {
     int tw = -1, tb = -1;
     attach_time(tw, tb, p + ".time_mlp.1", enc_out[i]);
     int li = add_conv(p + ".ops.0", C, enc_out[i], enc_k[i], 2, enc_p[i]);
+    if (i == 0 && fold_stem) {  // composite layer: reads the packed network input directly
+      ConvLayer& c0 = convs[li];
+      c0.comp_wi = stem_w; c0.comp_bi = stem_b; c0.comp_cm = dim;
+      c0.Cin = cin + 1; c0.Cpad = round_up(cin + 1, 8);
+      c0.K = c0.KH * c0.KW * c0.Cpad; c0.Kpad = round_up(c0.K, 32);
+      c0.wu_off = -1;
+      x = b_in;
+    }
     H /= 2; W /= 2;
     if (i < 5) {
       attach_bn(convs[li], p + ".ops.1");
@@ -290,11 +319,16 @@ int Net::finalize(cudaStream_t s) {
   if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
   for (auto& c : convs) {
     if (c.wu_off >= 0) {
-      int rcu = launch_repack_umma(packed + params[c.w].off, wq_umma + c.wu_off, c.Cout, c.Cin, c.standardize ? 1 : 0, s);
+      int rcu = launch_repack_umma(packed + params[c.w].off, wq_umma + c.wu_off, c.Cout, c.Cin, c.KH, c.stride, c.pad,
+                                   c.standardize ? 1 : 0, s);
       if (rcu) return rcu;
     }
-    int rc = launch_repack_conv(packed + params[c.w].off, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
-                                c.standardize ? 1 : 0, s);
+    int rc = c.comp_wi >= 0
+                 ? launch_compose_conv(packed + params[c.w].off, packed + params[c.comp_wi].off,
+                                       packed + params[c.comp_bi].off, wq + c.wq_off, c.Cout, c.comp_cm, c.Cin - 1, c.KH,
+                                       c.KW, c.Cpad, c.Kpad, s)
+                 : launch_repack_conv(packed + params[c.w].off, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
+                                      c.standardize ? 1 : 0, s);
     if (rc) return rc;
     const float* bias = c.b >= 0 ? packed + params[c.b].off : nullptr;
     const bool bn = c.bn_g >= 0;
@@ -319,13 +353,18 @@ size_t Net::workspace_bytes(int rows) const {
   size_t total = 0;
   total += 2 * align256((size_t)tab_floats_per_row * rows * sizeof(float));
   total += align256((size_t)stats_floats_per_row * rows * sizeof(float));
+  total += align256((size_t)time_dim * rows * sizeof(float));
   for (auto& b : bufs) total += align256(b.row_bytes() * rows);
   return total + 256;
 }
 
 int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
                  const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s, int noise_src, float noise_w,
-                 int src_rows) {
+                 int src_rows, int group_rows) {
+  // `group_rows` consecutive rows share one time value (and hence one set of epilogue tables): `time` then holds
+  // rows / group_rows entries (the sampler's logical calls); 1 = one time per row (the public forward)
+  if (group_rows < 1 || rows % group_rows) { set_error("internal: bad group_rows"); return DYF_ERR_ARG; }
+  const int tab_rows = rows / group_rows;
   if (!finalized) { set_error("net not finalized (call dyf_net_finalize after loading parameters)"); return DYF_ERR_STATE; }
   if (rows <= 0) { set_error("rows must be positive"); return DYF_ERR_ARG; }
   if (ws_bytes < workspace_bytes(rows)) { set_error("workspace too small"); return DYF_ERR_ARG; }
@@ -347,6 +386,8 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
   base += align256((size_t)tab_floats_per_row * rows * sizeof(float));
   float* stats = reinterpret_cast<float*>(base);
   base += align256((size_t)stats_floats_per_row * rows * sizeof(float));
+  float* temb = reinterpret_cast<float*>(base);
+  base += align256((size_t)time_dim * rows * sizeof(float));
   std::vector<__nv_bfloat16*> bp(bufs.size());
   for (size_t i = 0; i < bufs.size(); ++i) {
     bp[i] = reinterpret_cast<__nv_bfloat16*>(base);
@@ -364,7 +405,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
     }
     tp.dim = d.dim; tp.time_dim = time_dim;
     tp.layers = d_time_layers; tp.n_layers = (int)time_layers.size();
-    tp.rows = rows; tp.tabA = tabA; tp.tabB = tabB;
+    tp.rows = tab_rows; tp.tabA = tabA; tp.tabB = tabB; tp.temb = temb; tp.total_ch = (int)tab_floats_per_row;
     int rc = launch_time_tables(tp, s);
     if (rc) return rc;
   }
@@ -372,13 +413,27 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
   for (const Op& o : ops) {
     int rc = 0;
     switch (o.type) {
+      case OP_STEM: {
+        const ConvLayer& c = convs[o.layer];
+        StemParams p{};
+        for (int i = 0; i < nsrc; ++i) { p.pk.src[i] = srcs[i]; p.pk.C[i] = src_ch[i]; }
+        p.pk.nsrc = nsrc; p.pk.src_rows = src_rows > 0 ? src_rows : rows; p.pk.rows = rows;
+        p.pk.Hi = d.height; p.pk.Wi = d.width; p.pk.Ho = bufs[o.out].H; p.pk.Wo = bufs[o.out].W;
+        p.pk.bilinear = o.bilinear; p.pk.noise_src = -1;
+        p.w = packed + params[c.w].off; p.bias = packed + params[c.b].off; p.out = bp[o.out];
+        p.Cin = c.Cin; p.Cout = c.Cout;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        if (noise_src >= 0) { set_error("data+noise conditioning is not supported by the fused stem"); return DYF_ERR_UNSUPPORTED; }
+        rc = launch_stem(p, s);
+        break;
+      }
       case OP_PACK: {
         PackParams p{};
         for (int i = 0; i < nsrc; ++i) { p.src[i] = srcs[i]; p.C[i] = src_ch[i]; }
         p.nsrc = nsrc; p.src_rows = src_rows > 0 ? src_rows : rows; p.rows = rows; p.Hi = d.height; p.Wi = d.width;
         p.Ho = bufs[o.out].H; p.Wo = bufs[o.out].W; p.Cpad = bufs[o.out].C;
         p.bilinear = o.bilinear; p.out = bp[o.out];
-        p.noise_src = noise_src; p.noise_w = noise_w; p.seed = seed; p.stream = stream_id;
+        p.noise_src = noise_src; p.noise_w = noise_w; p.seed = seed; p.stream = stream_id; p.ones_channel = o.ones_channel;
         if (noise_src >= 0 && o.bilinear) { set_error("data+noise conditioning with an outer resize is unsupported"); return DYF_ERR_UNSUPPORTED; }
         rc = launch_pack(p, s);
         break;
@@ -393,8 +448,9 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
         p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;
-        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * rows;
-        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * rows;
+        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.tab_div = group_rows;
         p.act = o.act; p.M = (long long)rows * p.Ho * p.Wo;
         p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
         if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
@@ -421,12 +477,13 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.x = bp[o.in0]; p.y = bp[o.out];
         p.gamma = packed + params[n.g].off; p.beta = packed + params[n.b].off;
         if (n.table >= 0) {
-          p.tabA = tabA + (size_t)time_layers[n.table].tab_off * rows;
-          p.tabB = tabB + (size_t)time_layers[n.table].tab_off * rows;
+          p.tabA = tabA + (size_t)time_layers[n.table].tab_off * tab_rows;
+          p.tabB = tabB + (size_t)time_layers[n.table].tab_off * tab_rows;
         }
         if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
         p.stats = stats + (size_t)n.stats_off * rows;
         p.rows = rows; p.HW = bufs[o.in0].H * bufs[o.in0].W; p.C = n.C; p.G = n.G; p.act = o.act; p.eps = 1e-5f;
+        p.tab_div = group_rows;
         p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
         rc = launch_groupnorm(p, s);
         break;

@@ -117,10 +117,10 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     if (f_cond_first) push_cond();
     srcs[ns] = x_s; ch[ns++] = C;
     if (!f_cond_first) push_cond();
-    int rc = launch_fill(tbuf, (float)tF[idx], rows, s);
+    int rc = launch_fill(tbuf, (float)tF[idx], 1, s);
     if (rc) return rc;
     dyf_dropout dr{0, seed, call++};
-    return F->forward(rows, srcs, ch, ns, tbuf, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows);
+    return F->forward(rows, srcs, ch, ns, tbuf, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows);
   };
   // k logical interpolator calls at times t[0..k) sharing the inputs (ic, x0_hat); outputs land in ybuf[j]
   auto run_I = [&](const double* t, int k) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
@@ -132,12 +132,12 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     srcs[ns] = x0_hat; ch[ns++] = C;
     if (!i_cond_first && stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
     for (int j = 0; j < k; ++j) {
-      int rc = launch_fill(tbuf + (size_t)j * rows, (float)t[j], rows, s);
+      int rc = launch_fill(tbuf + j, (float)t[j], 1, s);
       if (rc) return rc;
     }
     dyf_dropout dr{d.enable_interpolator_dropout ? 1 : 0, seed, call};
     call += k;
-    return I->forward(k * rows, srcs, ch, ns, tbuf, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows);
+    return I->forward(k * rows, srcs, ch, ns, tbuf, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows);
   };
 
   for (int i = 0; i < n; ++i) {
