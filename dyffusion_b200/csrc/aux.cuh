@@ -76,6 +76,26 @@ struct ReadoutParams {
 };
 int launch_readout(const ReadoutParams& p, cudaStream_t s);
 
+// ---- attention blocks of the SST backbone (attn_kernels.cu)
+struct ChannelLNParams {
+  const __nv_bfloat16* x;  // [M, C]
+  __nv_bfloat16* y;        // [M, C]
+  const float* g;          // [C] gain
+  long long M;
+  int C;
+  DropCfg drop;            // dropout on the qkv-projection input (attention.py:13)
+};
+int launch_channel_ln(const ChannelLNParams& p, cudaStream_t s);
+struct AttnParams {
+  const __nv_bfloat16* qkv;  // [rows, n, 3 * heads * 32]
+  __nv_bfloat16* out;        // [rows, n, heads * 32]
+  float* ctx;                // linear attention scratch [rows, heads, 32, 32]
+  int rows, n, heads;
+  DropCfg drop;              // dropout on the attention probabilities (full attention, attention.py:59,70)
+};
+int launch_linear_attention(const AttnParams& p, cudaStream_t s);
+int launch_attention(const AttnParams& p, cudaStream_t s);
+
 // ---- time embedding -> per-layer epilogue tables
 struct TimeLayer {
   long long w_off;    // offset (floats) of Linear(time_dim, 2C).weight in the packed buffer, -1 = no time MLP

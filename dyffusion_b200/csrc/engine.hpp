@@ -63,12 +63,15 @@ struct Buf {
   size_t row_bytes() const { return (size_t)H * W * C * 2; }
 };
 
+struct LNLayer { int g = -1; int C = 0; };  // channel LayerNorm (gain only) in front of an attention block
+
 struct Net {
   dyf_net_desc d{};
   std::vector<ParamSlot> params;
   std::map<std::string, int> index;
   std::vector<ConvLayer> convs;
   std::vector<NormLayer> norms;
+  std::vector<LNLayer> lns;
   std::vector<Op> ops;
   std::vector<Buf> bufs;
   std::vector<TimeLayer> time_layers;
@@ -93,6 +96,8 @@ struct Net {
   int build_unet_simple();
   int build_convnet();
   int build_unet_resnet();
+  int resnet_block(const std::string& prefix, int x, int Cin, int Cout, int& site);
+  int attention_block(const std::string& prefix, int x, int C, bool linear, int& site);
   int add_conv(const std::string& wkey, int Cin, int Cout, int k, int stride, int pad, bool bias = true);
   void attach_bn(ConvLayer& c, const std::string& prefix);
   void attach_time(int& tw, int& tb, const std::string& prefix, int C);

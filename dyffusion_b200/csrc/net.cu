@@ -288,9 +288,157 @@ int Net::build_convnet() {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SST backbone (reference: src/models/unet.py:114-315; stage table SURVEY.md A.2)
+// ---------------------------------------------------------------------------------------------------------------
+// ResnetBlock (unet.py:79-109): block1 = WS-conv3x3 -> GroupNorm -> x*(scale+1)+shift -> SiLU -> Dropout(p1),
+// block2 = WS-conv3x3 -> GroupNorm -> SiLU -> Dropout(p2), output = block2 + residual_conv(x).
+int Net::resnet_block(const std::string& P, int x, int Cin, int Cout, int& site) {
+  const int H = bufs[x].H, W = bufs[x].W;
+  int tw = -1, tb = -1;
+  attach_time(tw, tb, P + ".mlp.1", Cout);
+  auto conv_gn = [&](const std::string& blk, int in, int cin, bool timed, float drop_p, int res) {
+    int li = add_conv(blk + ".proj", cin, Cout, 3, 1, 1);
+    convs[li].standardize = true;  // WeightStandardizedConv2d (:26-40), folded once at load time
+    int raw = add_buf(H, W, Cout);
+    Op c{}; c.type = OP_CONV; c.in0 = in; c.out = raw; c.layer = li; c.act = ACT_NONE;
+    ops.push_back(c);
+    NormLayer n; n.C = Cout; n.G = d.groups;
+    n.g = add_param(blk + ".norm.weight", {Cout});
+    n.b = add_param(blk + ".norm.bias", {Cout});
+    if (timed) { n.tw = tw; n.tb = tb; }
+    norms.push_back(n);
+    int y = add_buf(H, W, Cout);
+    Op g{}; g.type = OP_GROUPNORM; g.in0 = raw; g.out = y; g.layer = (int)norms.size() - 1; g.act = ACT_SILU;
+    g.drop_p = drop_p; g.site = site++; g.res = res;
+    ops.push_back(g);
+    return y;
+  };
+  const int h1 = conv_gn(P + ".block1", x, Cin, true, d.block_dropout1, BUF_NONE);
+  int res = x;
+  // parameters are registered in the reference's module order: mlp, block1, block2, residual_conv
+  const int h2_conv = add_conv(P + ".block2.proj", Cout, Cout, 3, 1, 1);
+  convs[h2_conv].standardize = true;
+  int raw2 = add_buf(H, W, Cout);
+  { Op c{}; c.type = OP_CONV; c.in0 = h1; c.out = raw2; c.layer = h2_conv; c.act = ACT_NONE; ops.push_back(c); }
+  NormLayer n2; n2.C = Cout; n2.G = d.groups;
+  n2.g = add_param(P + ".block2.norm.weight", {Cout});
+  n2.b = add_param(P + ".block2.norm.bias", {Cout});
+  norms.push_back(n2);
+  const int n2i = (int)norms.size() - 1;
+  if (Cin != Cout) {  // 1x1 residual projection (:96)
+    int li = add_conv(P + ".residual_conv", Cin, Cout, 1, 1, 0);
+    res = add_buf(H, W, Cout);
+    Op c{}; c.type = OP_CONV; c.in0 = x; c.out = res; c.layer = li; c.act = ACT_NONE;
+    ops.push_back(c);
+  }
+  int y = add_buf(H, W, Cout);
+  Op g{}; g.type = OP_GROUPNORM; g.in0 = raw2; g.out = y; g.layer = n2i; g.act = ACT_SILU; g.drop_p = d.block_dropout;
+  g.site = site++; g.res = res;
+  ops.push_back(g);
+  return y;
+}
+
+// Residual(PreNorm(LayerNorm, LinearAttention | Attention)) (unet.py:183-191, :209; attention.py)
+int Net::attention_block(const std::string& Q, int x, int C, bool linear, int& site) {
+  const int H = bufs[x].H, W = bufs[x].W, heads = 4, hidden = heads * 32;
+  LNLayer ln; ln.C = C;
+  ln.g = add_param(Q + ".fn.norm.g", {1, C, 1, 1});
+  lns.push_back(ln);
+  int y = add_buf(H, W, C);
+  Op l{}; l.type = OP_CHANNEL_LN; l.in0 = x; l.out = y; l.layer = (int)lns.size() - 1;
+  if (linear) { l.drop_p = d.attn_dropout; l.site = site++; }  // Dropout on the qkv input (attention.py:13)
+  ops.push_back(l);
+  int qi = add_conv(Q + (linear ? ".fn.fn.to_qkv.1" : ".fn.fn.to_qkv"), C, 3 * hidden, 1, 1, 0, /*bias=*/false);
+  int qkv = add_buf(H, W, 3 * hidden);
+  { Op c{}; c.type = OP_CONV; c.in0 = y; c.out = qkv; c.layer = qi; c.act = ACT_NONE; ops.push_back(c); }
+  int a = add_buf(H, W, hidden);
+  Op at{}; at.type = linear ? OP_LINATTN : OP_ATTN; at.in0 = qkv; at.out = a;
+  if (linear) at.aux = add_buf(1, 1, heads * 32 * 32 * 2);  // fp32 context matrices [heads, 32, 32]
+  else { at.drop_p = d.attn_dropout; at.site = site++; }   // Dropout on the probabilities (attention.py:59,70)
+  ops.push_back(at);
+  int oi = add_conv(Q + ".fn.fn.to_out", hidden, C, 1, 1, 0);
+  int out = add_buf(H, W, C);
+  { Op c{}; c.type = OP_CONV; c.in0 = a; c.out = out; c.layer = oi; c.act = ACT_NONE; c.res = x; ops.push_back(c); }
+  return out;
+}
+
 int Net::build_unet_resnet() {
-  set_error("unet.Unet (SST backbone) is not built yet in this round");
-  return DYF_ERR_UNSUPPORTED;
+  const int dim = d.dim, nres = d.n_mults;
+  const int cin = d.in_channels + d.cond_channels;
+  if (dim % 64 || nres < 1) { set_error("Unet: dim must be a multiple of 64"); return DYF_ERR_UNSUPPORTED; }
+  if (d.input_dropout > 0.f) { set_error("Unet: input_dropout > 0 is not built"); return DYF_ERR_UNSUPPORTED; }
+  if (d.groups != 8) { set_error("Unet: resnet_block_groups must be 8"); return DYF_ERR_UNSUPPORTED; }
+  Hin = d.height; Win = d.width;
+  int site = 1;
+  int xin = add_buf(Hin, Win, round_up(cin, 8));
+  Op pk{}; pk.type = OP_PACK; pk.out = xin; pk.bilinear = 0;
+  ops.push_back(pk);
+  int ci = add_conv("init_conv", cin, dim, d.init_kernel, d.init_stride, d.init_padding);
+  const int H0 = (Hin + 2 * d.init_padding - d.init_kernel) / d.init_stride + 1;
+  const int W0 = (Win + 2 * d.init_padding - d.init_kernel) / d.init_stride + 1;
+  int x = add_buf(H0, W0, dim);
+  { Op o{}; o.type = OP_CONV; o.in0 = xin; o.out = x; o.layer = ci; o.act = ACT_NONE; ops.push_back(o); }
+  const int r = x;  // `r = x.clone()` (:276)
+  std::vector<int> dims(nres + 1);
+  dims[0] = dim;
+  for (int i = 0; i < nres; ++i) dims[i + 1] = dim * d.dim_mults[i];
+  std::vector<int> hs;
+  for (int l = 0; l < nres; ++l) {
+    const int din = dims[l], dout = dims[l + 1];
+    const std::string P = "downs." + std::to_string(l);
+    x = resnet_block(P + ".0", x, din, din, site); hs.push_back(x);
+    x = resnet_block(P + ".1", x, din, din, site);
+    x = attention_block(P + ".2", x, din, true, site); hs.push_back(x);
+    const bool down = l < nres - 1 && !d.keep_spatial_dims;
+    int li = down ? add_conv(P + ".3", din, dout, 4, 2, 1) : add_conv(P + ".3", din, dout, 3, 1, 1);
+    int y = down ? add_buf((bufs[x].H + 2 - 4) / 2 + 1, (bufs[x].W + 2 - 4) / 2 + 1, dout) : add_buf(bufs[x].H, bufs[x].W, dout);
+    Op o{}; o.type = OP_CONV; o.in0 = x; o.out = y; o.layer = li; o.act = ACT_NONE;
+    ops.push_back(o);
+    x = y;
+  }
+  const int mid = dims[nres];
+  x = resnet_block("mid_block1", x, mid, mid, site);
+  x = attention_block("mid_attn", x, mid, false, site);
+  x = resnet_block("mid_block2", x, mid, mid, site);
+  auto concat = [&](int a, int b) {
+    if (bufs[a].H != bufs[b].H || bufs[a].W != bufs[b].W) return -1;
+    int y = add_buf(bufs[a].H, bufs[a].W, bufs[a].C + bufs[b].C);
+    Op u{}; u.type = OP_UPSAMPLE; u.in0 = a; u.in1 = b; u.out = y; u.c0 = bufs[a].C; u.c1 = bufs[b].C; u.scale = 1; u.bilinear = 0;
+    ops.push_back(u);
+    return y;
+  };
+  for (int l = 0; l < nres; ++l) {
+    const int din = dims[nres - 1 - l], dout = dims[nres - l];
+    const std::string P = "ups." + std::to_string(l);
+    for (int j = 0; j < 2; ++j) {
+      int cat = concat(x, hs.back());
+      hs.pop_back();
+      if (cat < 0) { set_error("Unet: skip connection grid mismatch (odd spatial size; reference fails too, SURVEY.md F4)"); return DYF_ERR_UNSUPPORTED; }
+      x = resnet_block(P + "." + std::to_string(j), cat, dout + din, dout, site);
+    }
+    x = attention_block(P + ".2", x, dout, true, site);
+    const bool up = l < nres - 1 && !d.keep_spatial_dims;
+    int in = x;
+    if (up) {  // nn.Upsample(scale_factor=2, mode="nearest") + Conv3x3 (:16-19)
+      in = add_buf(bufs[x].H * 2, bufs[x].W * 2, dout);
+      Op u{}; u.type = OP_UPSAMPLE; u.in0 = x; u.in1 = BUF_NONE; u.out = in; u.c0 = dout; u.c1 = 0; u.scale = 2; u.bilinear = 0;
+      ops.push_back(u);
+    }
+    int li = add_conv(up ? P + ".3.1" : P + ".3", dout, din, 3, 1, 1);
+    int y = add_buf(bufs[in].H, bufs[in].W, din);
+    Op o{}; o.type = OP_CONV; o.in0 = in; o.out = y; o.layer = li; o.act = ACT_NONE;
+    ops.push_back(o);
+    x = y;
+  }
+  int cat = concat(x, r);
+  if (cat < 0) { set_error("Unet: output grid differs from the stem grid"); return DYF_ERR_UNSUPPORTED; }
+  x = resnet_block("final_res_block", cat, 2 * dim, dim, site);
+  int fl = add_conv("final_conv", dim, d.out_channels, 1, 1, 0);
+  Op f{}; f.type = OP_CONV; f.in0 = x; f.layer = fl; f.out_mode = 2;
+  ops.push_back(f);
+  if (bufs[x].H != d.height || bufs[x].W != d.width) { set_error("Unet: init_stride != 1 is not built"); return DYF_ERR_UNSUPPORTED; }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -494,6 +642,25 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.rows = rows; p.Hs = bufs[o.in0].H; p.Ws = bufs[o.in0].W; p.Cin = bufs[o.in0].C; p.Cout = d.out_channels;
         p.Ho = d.height; p.Wo = d.width;
         rc = launch_readout(p, s);
+        break;
+      }
+      case OP_CHANNEL_LN: {
+        const LNLayer& l = lns[o.layer];
+        ChannelLNParams p{};
+        p.x = bp[o.in0]; p.y = bp[o.out]; p.g = packed + params[l.g].off;
+        p.M = (long long)rows * bufs[o.in0].H * bufs[o.in0].W; p.C = l.C;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        rc = launch_channel_ln(p, s);
+        break;
+      }
+      case OP_LINATTN:
+      case OP_ATTN: {
+        AttnParams p{};
+        p.qkv = bp[o.in0]; p.out = bp[o.out];
+        p.ctx = o.aux > 0 ? reinterpret_cast<float*>(bp[o.aux]) : nullptr;
+        p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.heads = 4;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        rc = o.type == OP_LINATTN ? launch_linear_attention(p, s) : launch_attention(p, s);
         break;
       }
       default: set_error("internal: unknown op"); return DYF_ERR_STATE;

@@ -35,7 +35,8 @@ def _build(dataset, role):
     return build_backbone(dataset, role, device="cpu")
 
 
-@pytest.mark.parametrize("dataset,role", [("ns", "F"), ("ns", "I"), ("spring", "F"), ("spring", "I")])
+@pytest.mark.parametrize("dataset,role", [("ns", "F"), ("ns", "I"), ("spring", "F"), ("spring", "I"), ("sst", "F"),
+                                          ("sst", "I")])
 def test_state_dict_contract(dataset, role):
     """Weight-layout contract: keys and shapes equal the reference's, so its checkpoints load."""
     m = _build(dataset, role)
