@@ -19,6 +19,12 @@
 // straight to an mbarrier), warp 12 owns TMEM and issues the MMAs (one thread), warp 13 streams weight tiles.
 // Two TMEM accumulators ping-pong, so the epilogue of tile i overlaps the MMAs of tile i+1 and the A/B rings
 // (3-4 patch stages, 6-8 weight stages, all on mbarriers) keep streaming across tile boundaries.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
 #include "conv.cuh"
 
 namespace dyf {
@@ -140,12 +146,17 @@ struct __align__(8) Barriers {
 // Persistent kernel: one CTA per SM walks the work list (n_tile fastest, so CTAs sharing an activation tile run
 // together and hit it in L2).  All pipelines run across tile boundaries: the A/B rings keep streaming into the next
 // tile while the epilogue warps drain the previous accumulator (two TMEM accumulators, ping-pong).
-template <int BN, int MODE, int AS, int BS>
+// TMA = true (S1K3 only): the halo patch of a chunk is ONE 4-D tensor-map copy (cp.async.bulk.tensor, box
+// 64 ch x 10 x 18 px, hardware zero fill outside the image) landing pixel-major with the 128-byte swizzle; taps are
+// still pure start-address shifts (+128 B per pixel) of a SWIZZLE_128B K-major descriptor with SBO = one patch row.
+template <int BN, int MODE, int AS, int BS, bool TMA>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
-                                                              int tiles_x, int tiles_y, int n_tiles, int num_work) {
+                                                              int tiles_x, int tiles_y, int n_tiles, int num_work,
+                                                              const __grid_constant__ CUtensorMap tmap, int base_off_mode) {
   using G = Geo<MODE>;
   using S = Sizes<MODE>;
-  constexpr int PLANE = S::PLANE, A_STAGE = S::A_STAGE, KSTEPS = S::KSTEPS;
+  constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
+  constexpr int A_STAGE = TMA ? ((G::PIX * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
   constexpr int B_TAP = BN * G::CH * 2;    // one tap of one chunk: [k8][BN rows][16 B]
   constexpr int B_STAGE = G::GT * B_TAP;   // a weight stage carries one filter row (GT taps)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   const int tiles_per_row = tiles_x * tiles_y;
 
   if (tid == 0) {
-    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TMA ? 1 : 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
     for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,6 +270,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   } else if (warp < EPI_WARPS + 4) {
     // =============================== A producers: halo patches via cp.async (zero fill = padding) ================
     const int ptid = tid - EPI_WARPS * 32;
+    if constexpr (TMA) {
+      if (ptid == 0) {
+        int ca = 0;
+        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+          int n_tile, row, oy0, ox0;
+          decode(w, n_tile, row, oy0, ox0);
+          for (int c = 0; c < nchunks; ++c, ++ca) {
+            const int st = ca % AS;
+            mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&bars->a_full[st]);
+            mbar_expect_tx(bar, G::PIX * 128);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                ::"r"(smem_u32(sA + st * A_STAGE)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * G::CH),
+                  "r"(G::in_x(ox0, 0)), "r"(G::in_y(oy0, 0)), "r"(row), "r"(bar) : "memory");
+          }
+        }
+      }
+    } else {
     constexpr int PSTEP = 128 / G::CPL;                     // patch pixels covered per pass of the 128 threads
     constexpr int ITERS = (G::PIX + PSTEP - 1) / PSTEP;
     const int g8 = ptid % G::CPL;                           // fixed 8-channel group of this thread
@@ -300,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
         cp_async_arrive_noinc(smem_u32(&bars->a_full[st]));
       }
     }
+    }
   } else if (warp == EPI_WARPS + 4) {
     // =============================== MMA issuer (one elected thread) ==============================================
     // The issue loop is latency-critical (one thread feeds the whole tensor pipe): descriptors are advanced by adding
@@ -308,9 +339,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_hi = (uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14);          // SBO | version 1 (bit 46)
+      // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
+      const uint32_t a_hi = TMA ? ((uint32_t)(((G::PW * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
+                                : ((uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14));
       const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
-      const uint32_t a_lo0 = ((uint32_t)(PLANE >> 4) << 16) | (smem_u32(sA) >> 4);      // LBO | start address
+      const uint32_t a_lo0 = ((uint32_t)(TMA ? 1 : (PLANE >> 4)) << 16) | (smem_u32(sA) >> 4);  // LBO | start address
       const uint32_t b_lo0 = ((uint32_t)((BN * 16) >> 4) << 16) | (smem_u32(sB) >> 4);
       const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
       const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
@@ -334,9 +367,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
               const int tap = g * G::GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
 #pragma unroll
               for (int ks = 0; ks < KSTEPS; ++ks) {  // one chunk = KSTEPS x (K = 16)
-                const uint32_t alo = a_lo + ((G::tap_offset(ky, kx, PLANE) + ks * 2 * PLANE) >> 4);
+                const int a_off = TMA ? (ky * G::PW + kx) * 128 + ks * 32 : G::tap_offset(ky, kx, PLANE) + ks * 2 * PLANE;
+                const uint32_t alo = a_lo + (a_off >> 4);
                 const uint32_t blo = b_lo + ((t * B_TAP + ks * 2 * (BN * 16)) >> 4);
-                const uint64_t ad = ((uint64_t)a_hi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
+                // base_offset (bits 49-51): phase of the 1024-byte swizzle pattern at the (unaligned) tap start
+                const uint32_t ahi = (TMA && base_off_mode) ? (a_hi | ((uint32_t)((a_off >> 7) & 7) << 17)) : a_hi;
+                const uint64_t ad = ((uint64_t)ahi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
                 umma_bf16(tmem_acc, ad, bd, idesc, (tap | ks) ? 1u : (uint32_t)(c != 0));
               }
             }
@@ -401,23 +437,58 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 }
 
 template <int MODE, int BN> struct Stages;  // pipeline depths that fill the 227 KB of one SM
-template <> struct Stages<S1K3, 64> { static constexpr int A = 3, B = 4; };   //  70 KB patches +  96 KB weights
+template <> struct Stages<S1K3, 64> { static constexpr int A = 6, B = 3; };   // 139 KB patches +  72 KB weights
 template <> struct Stages<S1K3, 128> { static constexpr int A = 3, B = 3; };  //  70 KB patches + 144 KB weights
-template <> struct Stages<S2K4, 64> { static constexpr int A = 3, B = 4; };   // 118 KB patches +  64 KB weights
+template <> struct Stages<S2K4, 64> { static constexpr int A = 4, B = 3; };   // 157 KB patches +  48 KB weights
 template <> struct Stages<S2K4, 128> { static constexpr int A = 3, B = 3; };  // 118 KB patches +  96 KB weights
 
-template <int BN, int MODE>
-int launch_t(const ConvParams& p, cudaStream_t stream) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 4-D tensor map over a bf16 NHWC activation tensor [rows, H, W, C]: box = 64 channels x PW x PH pixels, 128-B swizzle,
+// zero fill out of bounds (= the convolution's zero padding).
+static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return -1;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  using Key = std::tuple<const void*, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.rows};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)pw, (cuuint32_t)ph, 1};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(p.in), gdim, gstr, box, est,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return -1;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN, int MODE, bool TMA>
+int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap, int base_off_mode) {
   using G = Geo<MODE>;
-  constexpr int AS = Stages<MODE, BN>::A, BS = Stages<MODE, BN>::B;
-  constexpr int smem = AS * Sizes<MODE>::A_STAGE + BS * G::GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
+  constexpr int AS = TMA ? Stages<MODE, BN>::A : Stages<MODE, BN>::A, BS = Stages<MODE, BN>::B;
+  constexpr int a_stage = TMA ? ((G::PIX * 128 + 1023) / 1024) * 1024 : Sizes<MODE>::A_STAGE;
+  constexpr int smem = AS * a_stage + BS * G::GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     DYF_CUDA_OK(cudaGetDevice(&dev));
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W, tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
   const int n_tiles = p.Cout / BN;
@@ -427,7 +498,8 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_umma_kernel<BN, MODE, AS, BS><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work);
+  conv_umma_kernel<BN, MODE, AS, BS, TMA><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work,
+                                                                        tmap, base_off_mode);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -456,8 +528,19 @@ bool conv_umma_eligible(const ConvParams& p) {
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
   const bool n64 = umma_tile_n(p.Cout) == 64;
-  if (mode_of(p.KH, p.stride, p.pad) == S1K3) return n64 ? launch_t<64, S1K3>(p, stream) : launch_t<128, S1K3>(p, stream);
-  return n64 ? launch_t<64, S2K4>(p, stream) : launch_t<128, S2K4>(p, stream);
+  static const CUtensorMap dummy{};
+  if (mode_of(p.KH, p.stride, p.pad) == S1K3) {
+    static const char* env_a = getenv("DYF_UMMA_A");       // "cpasync" forces the cp.async patch gather
+    static const char* env_bo = getenv("DYF_UMMA_BASEOFF");
+    const bool want_tma = !(env_a && env_a[0] == 'c');
+    CUtensorMap tm;
+    if (want_tma && make_patch_tmap(p, Geo<S1K3>::PW, Geo<S1K3>::PH, &tm) == 0) {
+      const int bo = env_bo ? atoi(env_bo) : 0;
+      return n64 ? launch_t<64, S1K3, true>(p, stream, tm, bo) : launch_t<128, S1K3, true>(p, stream, tm, bo);
+    }
+    return n64 ? launch_t<64, S1K3, false>(p, stream, dummy, 0) : launch_t<128, S1K3, false>(p, stream, dummy, 0);
+  }
+  return n64 ? launch_t<64, S2K4, false>(p, stream, dummy, 0) : launch_t<128, S2K4, false>(p, stream, dummy, 0);
 }
 
 int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
