@@ -124,6 +124,55 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One filter tap = KSTEPS back-to-back MMAs (K = 16 each) whose descriptors differ by compile-time constants; issued
+// from ONE asm block by the elected lane so that no per-MMA election / convergence code is generated.
+template <int KSTEPS, int AK, int BK>
+__device__ __forceinline__ void umma_tap(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc_first,
+                                         uint32_t leader) {
+  static_assert(KSTEPS == 2 || KSTEPS == 4, "unsupported chunk depth");
+  if constexpr (KSTEPS == 4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pl, pa, pt;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 pl, %5, 0;\n\t"
+        "setp.ne.b32 pa, %4, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u64 a1, %1, %6;\n\t add.u64 a2, a1, %6;\n\t add.u64 a3, a2, %6;\n\t"
+        "add.u64 b1, %2, %7;\n\t add.u64 b2, b1, %7;\n\t add.u64 b3, b2, %7;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t"
+        "}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_first), "r"(leader), "n"((long long)AK), "n"((long long)BK)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pl, pa, pt;\n\t"
+        ".reg .b64 a1, b1;\n\t"
+        "setp.ne.b32 pl, %5, 0;\n\t"
+        "setp.ne.b32 pa, %4, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u64 a1, %1, %6;\n\t"
+        "add.u64 b1, %2, %7;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+        "}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_first), "r"(leader), "n"((long long)AK), "n"((long long)BK)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %1, 0;\n\t"
+      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 version bits = 1):
 //   addr(row, k16half) = start + (row % 8) * 16 + (row / 8) * SBO + k16half * LBO
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
@@ -152,7 +201,7 @@ struct __align__(8) Barriers {
 template <int BN, int MODE, int AS, int BS, bool TMA>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
-                                                              const __grid_constant__ CUtensorMap tmap, int base_off_mode) {
+                                                              const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
   using S = Sizes<MODE>;
   constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
@@ -336,7 +385,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
     // The issue loop is latency-critical (one thread feeds the whole tensor pipe): descriptors are advanced by adding
     // compile-time constants to pre-built low words, taps are fully unrolled, and barriers are touched once per
     // filter row (GT taps x KSTEPS MMAs) rather than once per tap.
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop; only the elected lane's tcgen05 instructions are predicated on.
+    {
+      const uint32_t leader = elect_one();
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
@@ -347,6 +398,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       const uint32_t b_lo0 = ((uint32_t)((BN * 16) >> 4) << 16) | (smem_u32(sB) >> 4);
       const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
       const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+      constexpr int AK = (TMA ? 32 : 2 * PLANE) >> 4;  // descriptor step between the K = 16 slices of a chunk
+      constexpr int BK = (2 * BN * 16) >> 4;
       int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;  // ring positions / phase parities
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -356,33 +409,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(bar_a_full + sa * 8, pa);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + sa * (A_STAGE >> 4);
+          const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (A_STAGE >> 4));
 #pragma unroll
           for (int g = 0; g < G::TAPS / G::GT; ++g) {
             mbar_wait(bar_b_full + sb * 8, pb);
             tc_fence_after();
-            const uint32_t b_lo = b_lo0 + sb * (B_STAGE >> 4);
+            const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_STAGE >> 4));
 #pragma unroll
             for (int t = 0; t < G::GT; ++t) {
               const int tap = g * G::GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
-#pragma unroll
-              for (int ks = 0; ks < KSTEPS; ++ks) {  // one chunk = KSTEPS x (K = 16)
-                const int a_off = TMA ? (ky * G::PW + kx) * 128 + ks * 32 : G::tap_offset(ky, kx, PLANE) + ks * 2 * PLANE;
-                const uint32_t alo = a_lo + (a_off >> 4);
-                const uint32_t blo = b_lo + ((t * B_TAP + ks * 2 * (BN * 16)) >> 4);
-                // base_offset (bits 49-51): phase of the 1024-byte swizzle pattern at the (unaligned) tap start
-                const uint32_t ahi = (TMA && base_off_mode) ? (a_hi | ((uint32_t)((a_off >> 7) & 7) << 17)) : a_hi;
-                const uint64_t ad = ((uint64_t)ahi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
-                umma_bf16(tmem_acc, ad, bd, idesc, (tap | ks) ? 1u : (uint32_t)(c != 0));
-              }
+              const int a_off = TMA ? (ky * G::PW + kx) * 128 : G::tap_offset(ky, kx, PLANE);
+              umma_tap<KSTEPS, AK, BK>(tmem_acc, a_st + (uint64_t)(a_off >> 4), b_st + (uint64_t)((t * B_TAP) >> 4), idesc,
+                                       tap ? 1u : (uint32_t)(c != 0), leader);
             }
-            umma_commit(bar_b_empty + sb * 8);  // weight stage free once these MMAs retire
+            umma_commit_if(bar_b_empty + sb * 8, leader);  // weight stage free once these MMAs retire
             if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          umma_commit(bar_a_empty + sa * 8);    // patch stage free
+          umma_commit_if(bar_a_empty + sa * 8, leader);    // patch stage free
           if (++sa == AS) { sa = 0; pa ^= 1; }
         }
-        umma_commit(smem_u32(&bars->acc_full[acc]));  // accumulator complete -> epilogue
+        umma_commit_if(smem_u32(&bars->acc_full[acc]), leader);  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -477,7 +523,7 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
 }
 
 template <int BN, int MODE, bool TMA>
-int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap, int base_off_mode) {
+int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap) {
   using G = Geo<MODE>;
   constexpr int AS = TMA ? Stages<MODE, BN>::A : Stages<MODE, BN>::A, BS = Stages<MODE, BN>::B;
   constexpr int a_stage = TMA ? ((G::PIX * 128 + 1023) / 1024) * 1024 : Sizes<MODE>::A_STAGE;
@@ -499,7 +545,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap, 
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
   conv_umma_kernel<BN, MODE, AS, BS, TMA><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work,
-                                                                        tmap, base_off_mode);
+                                                                        tmap);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -531,16 +577,15 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   static const CUtensorMap dummy{};
   if (mode_of(p.KH, p.stride, p.pad) == S1K3) {
     static const char* env_a = getenv("DYF_UMMA_A");       // "cpasync" forces the cp.async patch gather
-    static const char* env_bo = getenv("DYF_UMMA_BASEOFF");
     const bool want_tma = !(env_a && env_a[0] == 'c');
     CUtensorMap tm;
-    if (want_tma && make_patch_tmap(p, Geo<S1K3>::PW, Geo<S1K3>::PH, &tm) == 0) {
-      const int bo = env_bo ? atoi(env_bo) : 0;
-      return n64 ? launch_t<64, S1K3, true>(p, stream, tm, bo) : launch_t<128, S1K3, true>(p, stream, tm, bo);
-    }
-    return n64 ? launch_t<64, S1K3, false>(p, stream, dummy, 0) : launch_t<128, S1K3, false>(p, stream, dummy, 0);
+    // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
+    //  and UMMA reads alike -- verified on hardware)
+    if (want_tma && make_patch_tmap(p, Geo<S1K3>::PW, Geo<S1K3>::PH, &tm) == 0)
+      return n64 ? launch_t<64, S1K3, true>(p, stream, tm) : launch_t<128, S1K3, true>(p, stream, tm);
+    return n64 ? launch_t<64, S1K3, false>(p, stream, dummy) : launch_t<128, S1K3, false>(p, stream, dummy);
   }
-  return n64 ? launch_t<64, S2K4, false>(p, stream, dummy, 0) : launch_t<128, S2K4, false>(p, stream, dummy, 0);
+  return n64 ? launch_t<64, S2K4, false>(p, stream, dummy) : launch_t<128, S2K4, false>(p, stream, dummy);
 }
 
 int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
