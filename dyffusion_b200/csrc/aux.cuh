@@ -16,6 +16,8 @@ struct PackParams {
   __nv_bfloat16* out;
   // "data+noise" forecaster conditioning (dyffusion.py:220-227): src[noise_src] <- w*src + (1-w)*N(0,1)
   int ones_channel;        // output channel set to 1.0 inside the image (carries a folded bias), -1 = none
+  int s2d;                 // 1: space-to-depth packing -- output pixel (by, bx) holds the 2x2 block of the (resized)
+                           //    grid as 4 sub-positions x 16 channel slots (slot `ones_channel` of each = 1.0)
   int noise_src;           // -1 = none
   float noise_w;
   uint64_t seed, stream;
@@ -75,6 +77,18 @@ struct ReadoutParams {
   int rows, Hs, Ws, Cin, Cout, Ho, Wo;
 };
 int launch_readout(const ReadoutParams& p, cudaStream_t s);
+// Two-step readout: the channel contraction of the transposed conv runs on the tensor cores as a 1x1 conv
+// 64 -> 16 * Cout (z[pixel][(ky*4+kx)*Cout + co] = sum_ci x[pixel][ci] * Wt[ci][co][ky][kx]); this kernel then gathers, for
+// every output pixel, the 2x2 bilinear corners x 2x2 valid taps from z and adds the bias.
+struct ReadoutGatherParams {
+  const __nv_bfloat16* z;  // [rows, Hs, Ws, 16 * Cout]
+  const float* bias;       // [Cout]
+  float* y;                // [rows, Cout, Ho, Wo]
+  int rows, Hs, Ws, Cout, Ho, Wo;
+};
+int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s);
+// ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] -> 1x1-conv weight [16 * Cout, Cin] (row (ky*4+kx)*Cout + co)
+int launch_convt_to_conv1x1(const float* wt, float* out, int Cin, int Cout, cudaStream_t s);  // -> fp32 [16*Cout, Cin]
 
 // ---- attention blocks of the SST backbone (attn_kernels.cu)
 struct ChannelLNParams {
@@ -129,6 +143,10 @@ int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH,
 // channels + one "ones" channel carrying bi (zero outside the image, like the padded 1x1 output)
 int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_bfloat16* out, int O, int Cm, int Cs,
                         int KH, int KW, int Cpad, int Kpad, cudaStream_t s);
+// composite of (1x1 conv Wi,bi : Cs -> Cm) and (4x4/s2/p1 conv W0 : Cm -> O) expressed as a 3x3/s1/p1 conv over the
+// space-to-depth packed input (4 sub-positions x 16 slots = 64 channels): fp32 [O, 64, 3, 3]
+int launch_compose_s2d(const float* w0, const float* wi, const float* bi, float* out, int O, int Cm, int Cs,
+                       cudaStream_t s);
 // folded affine of conv-bias + eval BatchNorm: na = g*rsqrt(var+eps), nb = (bias-mean)*na + beta (bn may be null)
 int launch_fold_norm(const float* bias, const float* g, const float* beta, const float* mean, const float* var,
                      float eps, float* na, float* nb, int C, cudaStream_t s);

@@ -67,6 +67,51 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ pack, space-to-depth
+// One thread per (block pixel, sub-position): 16 channel slots = C_in resized input channels, a ones slot, zeros.
+__global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p) {
+  const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int sub = (int)(idx & 3);
+  const long long blk = idx >> 2;
+  const int bx = (int)(blk % p.Wo);
+  const int by = (int)((blk / p.Wo) % p.Ho);
+  const int r = (int)(blk / ((long long)p.Wo * p.Ho));
+  const int oy = 2 * by + (sub >> 1), ox = 2 * bx + (sub & 1);  // pixel of the full (resized) grid
+  const int Hf = 2 * p.Ho, Wf = 2 * p.Wo;
+  int y0 = oy, y1 = oy, x0 = ox, x1 = ox;
+  float ly = 0.f, lx = 0.f;
+  if (p.bilinear) {
+    bilinear_coord(oy, p.Hi, (float)p.Hi / (float)Hf, y0, y1, ly);
+    bilinear_coord(ox, p.Wi, (float)p.Wi / (float)Wf, x0, x1, lx);
+  }
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const size_t plane = (size_t)p.Hi * p.Wi;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  int oc = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    const float* base = p.src[s] + (size_t)(r % p.src_rows) * p.C[s] * plane;
+    for (int c = 0; c < p.C[s]; ++c, ++oc) {
+      const float* pl = base + (size_t)c * plane;
+      const float val = p.bilinear ? w00 * __ldg(pl + (size_t)y0 * p.Wi + x0) + w01 * __ldg(pl + (size_t)y0 * p.Wi + x1) +
+                                         w10 * __ldg(pl + (size_t)y1 * p.Wi + x0) + w11 * __ldg(pl + (size_t)y1 * p.Wi + x1)
+                                   : __ldg(pl + (size_t)oy * p.Wi + ox);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == oc) v[i] = val;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i == p.ones_channel) v[i] = 1.f;
+  uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)blk * 64 + sub * 16);
+  o[0] = pack8(v);
+  o[1] = pack8(v + 8);
+}
+
 // ------------------------------------------------------------------------------------------------ fused stem
 // One warp = 32 consecutive output pixels.  Phase 1: lane p gathers (bilinear) the C_in input values of pixel p --
 // neighbouring lanes read neighbouring source addresses of the same channel plane, so the gathers coalesce.
@@ -380,6 +425,50 @@ __global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
   }
 }
 
+// readout, step 2: gather (one thread per output pixel and channel)
+__global__ void __launch_bounds__(256) readout_gather_kernel(const ReadoutGatherParams p) {
+  const long long total = (long long)p.rows * p.Ho * p.Wo * p.Cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % p.Cout);
+  const long long pix = idx / p.Cout;
+  const int ox = (int)(pix % p.Wo);
+  const int oy = (int)((pix / p.Wo) % p.Ho);
+  const int r = (int)(pix / ((long long)p.Wo * p.Ho));
+  const int H2 = 2 * p.Hs, W2 = 2 * p.Ws, ldz = 16 * p.Cout;
+  int Y[2], X[2];
+  float ly, lx;
+  bilinear_coord(oy, H2, (float)H2 / (float)p.Ho, Y[0], Y[1], ly);
+  bilinear_coord(ox, W2, (float)W2 / (float)p.Wo, X[0], X[1], lx);
+  const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
+  const __nv_bfloat16* zr = p.z + (size_t)r * p.Hs * p.Ws * ldz + co;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int yy = Y[a], xx = X[b];
+      float v = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ky = ((yy + 1) & 1) + 2 * dy, kx = ((xx + 1) & 1) + 2 * dx;
+          const int iy = (yy + 1 - ky) >> 1, ix = (xx + 1 - kx) >> 1;
+          if (iy >= 0 && iy < p.Hs && ix >= 0 && ix < p.Ws)
+            v += __bfloat162float(zr[((size_t)iy * p.Ws + ix) * ldz + (ky * 4 + kx) * p.Cout]);
+        }
+      acc = fmaf(wy[a] * wx[b], v, acc);
+    }
+  p.y[(((size_t)r * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = acc + __ldg(p.bias + co);
+}
+
+__global__ void convt_to_conv1x1_kernel(const float* __restrict__ wt, float* __restrict__ out, int Cin, int Cout) {
+  const int j = blockIdx.x;  // output row (ky*4+kx)*Cout + co
+  const int co = j % Cout, kk = j / Cout;
+  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) out[(size_t)j * Cin + ci] = wt[((size_t)ci * Cout + co) * 16 + kk];
+}
+
 // ------------------------------------------------------------------------------------------------ time tables
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -532,6 +621,25 @@ __global__ void __launch_bounds__(256) compose_conv_kernel(const float* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) compose_s2d_kernel(const float* __restrict__ w0, const float* __restrict__ wi,
+                                                         const float* __restrict__ bi, float* __restrict__ out, int Cm,
+                                                         int Cs) {
+  const int o = blockIdx.x;
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) {
+    const int slot = i / 9, t = i - slot * 9;
+    const int sub = slot >> 4, c = slot & 15, dy = sub >> 1, dx = sub & 1, ty = t / 3, tx = t - ty * 3;
+    const int ky = 2 * (ty - 1) + dy + 1, kx = 2 * (tx - 1) + dx + 1;  // tap of the original 4x4 / stride-2 conv
+    float v = 0.f;
+    if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4 && c <= Cs) {
+      for (int m = 0; m < Cm; ++m) {
+        const float a = w0[(((size_t)o * Cm + m) * 4 + ky) * 4 + kx];
+        v = fmaf(a, c < Cs ? wi[(size_t)m * Cs + c] : bi[m], v);
+      }
+    }
+    out[(size_t)o * 576 + i] = v;
+  }
+}
+
 __global__ void fold_norm_kernel(const float* bias, const float* g, const float* beta, const float* mean,
                                  const float* var, float eps, float* na, float* nb, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -569,6 +677,16 @@ __global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
 }  // namespace
 
 int launch_pack(const PackParams& p, cudaStream_t s) {
+  if (p.s2d) {
+    int ctot = 0;
+    for (int i = 0; i < p.nsrc; ++i) ctot += p.C[i];
+    if (ctot > 15 || p.ones_channel != ctot || p.noise_src >= 0) { set_error("pack s2d: needs <= 15 input channels"); return -1; }
+    const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
+    ProfScope prof(s, KC_PACK);
+    pack_s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+    DYF_LAUNCH_OK("pack_s2d_kernel");
+    return 0;
+  }
   if (p.Cpad % 8 != 0) { set_error("pack: Cpad must be a multiple of 8"); return -1; }
   const long long total = (long long)p.rows * p.Ho * p.Wo;
   ProfScope prof(s, KC_PACK);
@@ -637,6 +755,20 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s) {
   return 0;
 }
 
+int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s) {
+  const long long total = (long long)p.rows * p.Ho * p.Wo * p.Cout;
+  ProfScope prof(s, KC_READOUT);
+  readout_gather_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  DYF_LAUNCH_OK("readout_gather_kernel");
+  return 0;
+}
+
+int launch_convt_to_conv1x1(const float* wt, float* out, int Cin, int Cout, cudaStream_t s) {
+  convt_to_conv1x1_kernel<<<16 * Cout, 64, 0, s>>>(wt, out, Cin, Cout);
+  DYF_LAUNCH_OK("convt_to_conv1x1_kernel");
+  return 0;
+}
+
 int launch_time_tables(const TimeParams& p, cudaStream_t s) {
   if (p.dim > 256 || p.time_dim > 512) { set_error("time tables: dim too large"); return -1; }
   if (p.n_layers == 0) return 0;
@@ -662,6 +794,13 @@ int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_
                         int KH, int KW, int Cpad, int Kpad, cudaStream_t s) {
   compose_conv_kernel<<<O, 256, 0, s>>>(w0, wi, bi, out, Cm, Cs, KH * KW, Cpad, Kpad);
   DYF_LAUNCH_OK("compose_conv_kernel");
+  return 0;
+}
+
+int launch_compose_s2d(const float* w0, const float* wi, const float* bi, float* out, int O, int Cm, int Cs,
+                       cudaStream_t s) {
+  compose_s2d_kernel<<<O, 256, 0, s>>>(w0, wi, bi, out, Cm, Cs);
+  DYF_LAUNCH_OK("compose_s2d_kernel");
   return 0;
 }
 

@@ -91,6 +91,7 @@ int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 bool conv_umma_eligible(const ConvParams& p);
 bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad);
+int umma_padded_cout(int Cout);
 int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
                        cudaStream_t s);
 

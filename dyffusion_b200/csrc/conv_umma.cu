@@ -34,7 +34,7 @@ constexpr int TILE_H = 16, TILE_W = 8;  // output pixels per CTA tile (M = 128)
 constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each draining half of the accumulator columns
 constexpr int THREADS = (EPI_WARPS + 4 + 2) * 32;  // epilogue + 4 producer warps + MMA warp + weight-stream warp
 
-enum Mode { S1K3 = 0, S2K4 = 1 };
+enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2 };
 
 template <int MODE> struct Geo;
 template <> struct Geo<S1K3> {
@@ -52,6 +52,18 @@ template <> struct Geo<S1K3> {
   __device__ static int plane_of(int g, int /*pc*/) { return g; }
   __device__ static int in_y(int oy0, int pr) { return oy0 - 1 + pr; }
   __device__ static int in_x(int ox0, int pc) { return ox0 - 1 + pc; }
+};
+template <> struct Geo<S1K1> {  // 1x1 convolution = plain GEMM over the 16 x 8 pixel tile (no halo, one "tap")
+  static constexpr int CH = 64, PLANES = 8, CPL = 8;
+  static constexpr int PH = TILE_H, PW = TILE_W;
+  static constexpr int PIX = PH * PW, SLOTS = PIX;
+  static constexpr int TAPS = 1, KW = 1, GT = 1;
+  static constexpr int SBO = PW * 16;
+  __device__ static int tap_offset(int, int, int) { return 0; }
+  __device__ static int slot(int pr, int pc) { return pr * PW + pc; }
+  __device__ static int plane_of(int g, int) { return g; }
+  __device__ static int in_y(int oy0, int pr) { return oy0 + pr; }
+  __device__ static int in_x(int ox0, int pc) { return ox0 + pc; }
 };
 template <> struct Geo<S2K4> {
   static constexpr int CH = 32;
@@ -270,6 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       const int cbeg = (warp >> 2) * COLS;
 #pragma unroll 2
       for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
+        if (n_tile * BN + c0 >= p.Cout) break;  // zero-padded output channels of a ragged last n-tile (warp-uniform)
         uint32_t v[8];
         tmem_ld8(taddr + c0, v);
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(tA + c0)), a1 = __ldg(reinterpret_cast<const float4*>(tA + c0 + 4));
@@ -459,7 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
 __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                          int O, int I, int BN, int taps, int ch, int standardize) {
   const int nchunks = I / ch, k8n = ch / 8;
-  const long long total = (long long)O * I * taps;
+  const long long total = (long long)((O + BN - 1) / BN * BN) * I * taps;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   long long r = idx;
@@ -470,6 +483,7 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
   const int chunk = (int)(r % nchunks); r /= nchunks;
   const int n_tile = (int)r;
   const int o = n_tile * BN + n, ci = chunk * ch + k8 * 8 + e;
+  if (o >= O) { out[idx] = __float2bfloat16_rn(0.f); return; }  // zero rows of a ragged last n-tile
   float v = w[((size_t)o * I + ci) * taps + tap];
   if (standardize) {  // WeightStandardizedConv2d (reference unet.py:32-40), recomputed per element (load-time only)
     const float* wo = w + (size_t)o * I * taps;
@@ -485,6 +499,8 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 template <int MODE, int BN> struct Stages;  // pipeline depths that fill the 227 KB of one SM
 template <> struct Stages<S1K3, 64> { static constexpr int A = 6, B = 3; };   // 139 KB patches +  72 KB weights
 template <> struct Stages<S1K3, 128> { static constexpr int A = 3, B = 3; };  //  70 KB patches + 144 KB weights
+template <> struct Stages<S1K1, 64> { static constexpr int A = 6, B = 4; };
+template <> struct Stages<S1K1, 128> { static constexpr int A = 6, B = 4; };
 template <> struct Stages<S2K4, 64> { static constexpr int A = 4, B = 3; };   // 157 KB patches +  48 KB weights
 template <> struct Stages<S2K4, 128> { static constexpr int A = 3, B = 3; };  // 118 KB patches +  96 KB weights
 
@@ -502,9 +518,9 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return -1;
     fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
-  using Key = std::tuple<const void*, int, int, int, int>;
+  using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
-  const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin};
+  const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin, pw, ph};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return 0; }
   cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.rows};
@@ -537,7 +553,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap) 
     DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W, tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
-  const int n_tiles = p.Cout / BN;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
   const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
   if (work > 0x7fffffffLL) { set_error("conv_umma: too many tiles"); return -1; }
   const int grid = (int)(work < num_sms ? work : num_sms);
@@ -553,16 +569,20 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap) 
 int mode_of(int k, int stride, int pad) {
   if (k == 3 && stride == 1 && pad == 1) return S1K3;
   if (k == 4 && stride == 2 && pad == 1) return S2K4;
+  if (k == 1 && stride == 1 && pad == 0) return S1K1;
   return -1;
 }
 
 }  // namespace
 
-int umma_tile_n(int Cout) { return Cout == 64 ? 64 : 128; }
+int umma_tile_n(int Cout) { return Cout <= 64 ? 64 : 128; }
+int umma_padded_cout(int Cout) { const int bn = umma_tile_n(Cout); return (Cout + bn - 1) / bn * bn; }
 
 bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad) {
   const int mode = mode_of(k, stride, pad);
-  if (mode < 0 || !(Cout == 64 || Cout % 128 == 0)) return false;
+  if (mode < 0 || Cout % 8 != 0) return false;
+  if (mode == S1K1) return Cin_pad % 64 == 0 && (Cout <= 64 || Cout % 128 == 0);
+  if (!(Cout == 64 || Cout % 128 == 0)) return false;
   return Cin_pad % (mode == S1K3 ? 64 : 32) == 0;
 }
 
@@ -575,15 +595,21 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
   const bool n64 = umma_tile_n(p.Cout) == 64;
   static const CUtensorMap dummy{};
-  if (mode_of(p.KH, p.stride, p.pad) == S1K3) {
-    static const char* env_a = getenv("DYF_UMMA_A");       // "cpasync" forces the cp.async patch gather
-    const bool want_tma = !(env_a && env_a[0] == 'c');
-    CUtensorMap tm;
-    // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
-    //  and UMMA reads alike -- verified on hardware)
+  const int mode = mode_of(p.KH, p.stride, p.pad);
+  static const char* env_a = getenv("DYF_UMMA_A");  // "cpasync" forces the cp.async patch gather
+  const bool want_tma = !(env_a && env_a[0] == 'c');
+  CUtensorMap tm;
+  // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
+  //  and UMMA reads alike -- verified on hardware)
+  if (mode == S1K3) {
     if (want_tma && make_patch_tmap(p, Geo<S1K3>::PW, Geo<S1K3>::PH, &tm) == 0)
       return n64 ? launch_t<64, S1K3, true>(p, stream, tm) : launch_t<128, S1K3, true>(p, stream, tm);
     return n64 ? launch_t<64, S1K3, false>(p, stream, dummy) : launch_t<128, S1K3, false>(p, stream, dummy);
+  }
+  if (mode == S1K1) {
+    if (want_tma && make_patch_tmap(p, Geo<S1K1>::PW, Geo<S1K1>::PH, &tm) == 0)
+      return n64 ? launch_t<64, S1K1, true>(p, stream, tm) : launch_t<128, S1K1, true>(p, stream, tm);
+    return n64 ? launch_t<64, S1K1, false>(p, stream, dummy) : launch_t<128, S1K1, false>(p, stream, dummy);
   }
   return n64 ? launch_t<64, S2K4, false>(p, stream, dummy) : launch_t<128, S2K4, false>(p, stream, dummy);
 }
@@ -592,8 +618,8 @@ int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, 
                        cudaStream_t s) {
   const int mode = mode_of(k, stride, pad);
   if (mode < 0) { set_error("repack_umma: unsupported geometry"); return -1; }
-  const int taps = k * k, ch = mode == S1K3 ? 64 : 32;
-  const long long total = (long long)O * I * taps;
+  const int taps = k * k, ch = mode == S2K4 ? 32 : 64;
+  const long long total = (long long)umma_padded_cout(O) * I * taps;
   repack_umma_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, O, I, umma_tile_n(O), taps, ch, standardize);
   DYF_LAUNCH_OK("repack_umma_kernel");
   return 0;

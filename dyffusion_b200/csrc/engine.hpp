@@ -28,6 +28,9 @@ struct ConvLayer {
   bool standardize = false;                   // WeightStandardizedConv2d
   int K = 0, Kpad = 0;
   size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
+  int convt_z = 0;                              // weight = ConvTranspose2d [Cin, Cout/16, 4, 4] re-laid out as a 1x1 conv
+  int comp_s2d = 0;                             // composite expressed as 3x3/s1 over the space-to-depth packed input
+  int flops_cin = 0;                            // channels to count per tap in FLOP accounting (0 = Cin)
   int comp_wi = -1, comp_bi = -1, comp_cm = 0;  // composite layer: preceded by a folded 1x1 conv (weights, bias, width)
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
@@ -41,7 +44,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
 constexpr int BUF_NONE = -1;
 
 struct Op {

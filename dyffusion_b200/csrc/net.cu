@@ -56,7 +56,7 @@ int Net::add_conv(const std::string& prefix, int Cin, int Cout, int k, int strid
   wq_elems += (size_t)Cout * c.Kpad;
   if (conv_umma_shape_ok(c.Cpad, Cout, k, stride, pad) && c.Cpad == Cin) {
     c.wu_off = (long long)wu_elems;
-    wu_elems += (size_t)Cout * Cin * k * k;
+    wu_elems += (size_t)umma_padded_cout(Cout) * Cin * k * k;
   }
   c.na_off = packed_floats + extra_floats;  // resolved against the final packed size in finalize()
   extra_floats += round_up(Cout, 4);
@@ -162,13 +162,17 @@ int Net::build_unet_simple() {
   // (zero in the padding, exactly like the padded stem output).  The 64-channel full-resolution stem output -- the
   // largest activation of the encoder -- is then never materialised.  Exact in real arithmetic.
   const bool fold_stem = d.input_dropout == 0.f;
+  // ... and when the input has <= 15 channels the composite runs on the tcgen05 3x3 kernel: the resized input is packed
+  // space-to-depth (2x2 blocks -> 4 x 16 channel slots at half resolution), which turns the 4x4 / stride-2 composite
+  // into a 3x3 / stride-1 conv over 64 channels with structurally-zero weights for the unused (block, sub-position) taps.
+  const bool stem_s2d = fold_stem && cin + 1 <= 16 && (dim * 2 == 64 || (dim * 2) % 128 == 0);
   int x = BUF_NONE;
   int stem_w = -1, stem_b = -1, b_in = BUF_NONE;
   if (fold_stem) {
     stem_w = add_param("init_conv.weight", {dim, cin, 1, 1});
     stem_b = add_param("init_conv.bias", {dim});
-    b_in = add_buf(Hin, Win, round_up(cin + 1, 8));
-    Op pk{}; pk.type = OP_PACK; pk.out = b_in; pk.bilinear = resize ? 1 : 0; pk.ones_channel = cin;
+    b_in = stem_s2d ? add_buf(Hin / 2, Win / 2, 64) : add_buf(Hin, Win, round_up(cin + 1, 8));
+    Op pk{}; pk.type = OP_PACK; pk.out = b_in; pk.bilinear = resize ? 1 : 0; pk.ones_channel = cin; pk.aux = stem_s2d ? 1 : 0;
     ops.push_back(pk);
   } else {
     int ci = add_conv("init_conv", cin, dim, 1, 1, 0);
@@ -197,9 +201,15 @@ int Net::build_unet_simple() {
     if (i == 0 && fold_stem) {  // composite layer: reads the packed network input directly
       ConvLayer& c0 = convs[li];
       c0.comp_wi = stem_w; c0.comp_bi = stem_b; c0.comp_cm = dim;
-      c0.Cin = cin + 1; c0.Cpad = round_up(cin + 1, 8);
-      c0.K = c0.KH * c0.KW * c0.Cpad; c0.Kpad = round_up(c0.K, 32);
-      c0.wu_off = -1;
+      if (stem_s2d) {
+        c0.comp_s2d = 1; c0.flops_cin = (16 * (cin + 1) + 8) / 9;
+        c0.Cin = c0.Cpad = 64; c0.KH = c0.KW = 3; c0.stride = 1; c0.pad = 1;
+        c0.K = c0.Kpad = 9 * 64;  // fits the 4x4 allocation made by add_conv (wq and the tcgen05 stage tiles)
+      } else {
+        c0.Cin = cin + 1; c0.Cpad = round_up(cin + 1, 8);
+        c0.K = c0.KH * c0.KW * c0.Cpad; c0.Kpad = round_up(c0.K, 32);
+        c0.wu_off = -1;
+      }
       x = b_in;
     }
     H /= 2; W /= 2;
@@ -248,10 +258,27 @@ int Net::build_unet_simple() {
     x = y;
   }
   // readout (:141-150) + outer resize back to the data grid (:195)
+  // The channel contraction of the ConvTranspose2d (64 -> 16 taps x Cout values per source pixel) runs as a 1x1 conv on
+  // the tensor cores; a gather kernel then evaluates only the transposed-conv pixels the final resize samples.
   ro_w = add_param("readout.0.weight", {dim, d.out_channels, 4, 4});
   ro_b = add_param("readout.0.bias", {d.out_channels});
-  Op r{}; r.type = OP_READOUT; r.in0 = x;
-  ops.push_back(r);
+  if (dim % 8 == 0 && (16 * d.out_channels) % 8 == 0) {
+    ConvLayer z;
+    z.w = ro_w; z.convt_z = 1;
+    z.Cin = z.Cpad = dim; z.Cout = 16 * d.out_channels; z.KH = z.KW = 1; z.stride = 1; z.pad = 0;
+    z.K = dim; z.Kpad = round_up(dim, 32);
+    z.wq_off = wq_elems; wq_elems += (size_t)z.Cout * z.Kpad;
+    if (conv_umma_shape_ok(z.Cpad, z.Cout, 1, 1, 0)) { z.wu_off = (long long)wu_elems; wu_elems += (size_t)umma_padded_cout(z.Cout) * z.Cin; }
+    convs.push_back(z);
+    int zb = add_buf(bufs[x].H, bufs[x].W, 16 * d.out_channels);
+    Op c{}; c.type = OP_CONV; c.in0 = x; c.out = zb; c.layer = (int)convs.size() - 1; c.act = ACT_NONE;
+    ops.push_back(c);
+    Op g{}; g.type = OP_READOUT_GATHER; g.in0 = zb;
+    ops.push_back(g);
+  } else {
+    Op r{}; r.type = OP_READOUT; r.in0 = x;
+    ops.push_back(r);
+  }
   return 0;
 }
 
@@ -466,18 +493,42 @@ int Net::finalize(cudaStream_t s) {
   if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
   if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
   for (auto& c : convs) {
+    if (c.convt_z) {  // ConvTranspose2d weight re-laid out as a 1x1 conv weight [16 * Cout_t, Cin] (fp32 staging)
+      float* wz = nullptr;
+      DYF_CUDA_OK(cudaMalloc(&wz, (size_t)c.Cout * c.Cin * sizeof(float)));
+      int rz = launch_convt_to_conv1x1(packed + params[c.w].off, wz, c.Cin, c.Cout / 16, s);
+      if (!rz) rz = launch_repack_conv(wz, wq + c.wq_off, c.Cout, c.Cin, 1, 1, c.Cpad, c.Kpad, 0, s);
+      if (!rz && c.wu_off >= 0) rz = launch_repack_umma(wz, wq_umma + c.wu_off, c.Cout, c.Cin, 1, 1, 0, 0, s);
+      if (!rz) rz = launch_fold_norm(nullptr, nullptr, nullptr, nullptr, nullptr, 1e-5f, packed + c.na_off, packed + c.nb_off, c.Cout, s);
+      if (rz) return rz;
+      DYF_CUDA_OK(cudaStreamSynchronize(s));
+      DYF_CUDA_OK(cudaFree(wz));
+      continue;
+    }
+    const float* w_src = packed + params[c.w].off;
+    float* composed = nullptr;
+    if (c.comp_s2d) {  // composite weights in plain conv layout [Cout, 64, 3, 3] (fp32 staging, freed below)
+      DYF_CUDA_OK(cudaMalloc(&composed, (size_t)c.Cout * 576 * sizeof(float)));
+      int rcc = launch_compose_s2d(packed + params[c.w].off, packed + params[c.comp_wi].off, packed + params[c.comp_bi].off,
+                                   composed, c.Cout, c.comp_cm, params[c.comp_wi].shape[1], s);
+      if (rcc) return rcc;
+      w_src = composed;
+    }
     if (c.wu_off >= 0) {
-      int rcu = launch_repack_umma(packed + params[c.w].off, wq_umma + c.wu_off, c.Cout, c.Cin, c.KH, c.stride, c.pad,
-                                   c.standardize ? 1 : 0, s);
+      int rcu = launch_repack_umma(w_src, wq_umma + c.wu_off, c.Cout, c.Cin, c.KH, c.stride, c.pad, c.standardize ? 1 : 0, s);
       if (rcu) return rcu;
     }
-    int rc = c.comp_wi >= 0
+    int rc = (c.comp_wi >= 0 && !c.comp_s2d)
                  ? launch_compose_conv(packed + params[c.w].off, packed + params[c.comp_wi].off,
                                        packed + params[c.comp_bi].off, wq + c.wq_off, c.Cout, c.comp_cm, c.Cin - 1, c.KH,
                                        c.KW, c.Cpad, c.Kpad, s)
-                 : launch_repack_conv(packed + params[c.w].off, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
+                 : launch_repack_conv(w_src, wq + c.wq_off, c.Cout, c.Cin, c.KH, c.KW, c.Cpad, c.Kpad,
                                       c.standardize ? 1 : 0, s);
     if (rc) return rc;
+    if (composed) {
+      DYF_CUDA_OK(cudaStreamSynchronize(s));
+      DYF_CUDA_OK(cudaFree(composed));
+    }
     const float* bias = c.b >= 0 ? packed + params[c.b].off : nullptr;
     const bool bn = c.bn_g >= 0;
     rc = launch_fold_norm(bias, bn ? packed + params[c.bn_g].off : nullptr, bn ? packed + params[c.bn_b].off : nullptr,
@@ -582,6 +633,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.Ho = bufs[o.out].H; p.Wo = bufs[o.out].W; p.Cpad = bufs[o.out].C;
         p.bilinear = o.bilinear; p.out = bp[o.out];
         p.noise_src = noise_src; p.noise_w = noise_w; p.seed = seed; p.stream = stream_id; p.ones_channel = o.ones_channel;
+        p.s2d = o.aux;
         if (noise_src >= 0 && o.bilinear) { set_error("data+noise conditioning with an outer resize is unsupported"); return DYF_ERR_UNSUPPORTED; }
         rc = launch_pack(p, s);
         break;
@@ -592,7 +644,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         ConvParams p{};
         p.in = bp[o.in0]; p.w = wq + c.wq_off;
         p.w_umma = (c.wu_off >= 0 && !getenv("DYF_DISABLE_UMMA")) ? wq_umma + c.wu_off : nullptr;
-        p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C; p.Cin_real = c.Cin;
+        p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C; p.Cin_real = c.flops_cin ? c.flops_cin : c.Cin;
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
         p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;
@@ -634,6 +686,13 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.tab_div = group_rows;
         p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
         rc = launch_groupnorm(p, s);
+        break;
+      }
+      case OP_READOUT_GATHER: {
+        ReadoutGatherParams p{};
+        p.z = bp[o.in0]; p.bias = packed + params[ro_b].off; p.y = y;
+        p.rows = rows; p.Hs = bufs[o.in0].H; p.Ws = bufs[o.in0].W; p.Cout = d.out_channels; p.Ho = d.height; p.Wo = d.width;
+        rc = launch_readout_gather(p, s);
         break;
       }
       case OP_READOUT: {
