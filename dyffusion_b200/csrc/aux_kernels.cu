@@ -88,25 +88,28 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p) {
   }
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const size_t plane = (size_t)p.Hi * p.Wi;
+  // flattened concat channel -> plane pointer (uniform, computed once per thread; nsrc <= 6, at most 15 channels)
+  const int o00 = y0 * p.Wi + x0, o01 = y0 * p.Wi + x1, o10 = y1 * p.Wi + x0, o11 = y1 * p.Wi + x1;
+  int cbeg[7];
+  cbeg[0] = 0;
+#pragma unroll
+  for (int s = 0; s < 6; ++s) cbeg[s + 1] = cbeg[s] + (s < p.nsrc ? p.C[s] : 0);
   float v[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  int oc = 0;
-  for (int s = 0; s < p.nsrc; ++s) {
-    const float* base = p.src[s] + (size_t)(r % p.src_rows) * p.C[s] * plane;
-    for (int c = 0; c < p.C[s]; ++c, ++oc) {
-      const float* pl = base + (size_t)c * plane;
-      const float val = p.bilinear ? w00 * __ldg(pl + (size_t)y0 * p.Wi + x0) + w01 * __ldg(pl + (size_t)y0 * p.Wi + x1) +
-                                         w10 * __ldg(pl + (size_t)y1 * p.Wi + x0) + w11 * __ldg(pl + (size_t)y1 * p.Wi + x1)
-                                   : __ldg(pl + (size_t)oy * p.Wi + ox);
+  for (int i = 0; i < 16; ++i) {  // compile-time slot index: all gathers are issued before any is consumed
+    float val = 0.f;
+    if (i < cbeg[6]) {
+      const float* sb = p.src[0];
+      int sc = p.C[0], s0 = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i == oc) v[i] = val;
+      for (int k = 1; k < 6; ++k)
+        if (k < p.nsrc && i >= cbeg[k]) { sb = p.src[k]; sc = p.C[k]; s0 = cbeg[k]; }
+      const float* pl = sb + ((size_t)(r % p.src_rows) * sc + (i - s0)) * plane;
+      val = p.bilinear ? w00 * __ldg(pl + o00) + w01 * __ldg(pl + o01) + w10 * __ldg(pl + o10) + w11 * __ldg(pl + o11)
+                       : __ldg(pl + (size_t)oy * p.Wi + ox);
     }
+    v[i] = i == p.ones_channel ? 1.f : val;
   }
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (i == p.ones_channel) v[i] = 1.f;
   uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)blk * 64 + sub * 16);
   o[0] = pack8(v);
   o[1] = pack8(v + 8);

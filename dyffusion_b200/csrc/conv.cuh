@@ -85,6 +85,30 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m,
   }
 }
 
+// Fused decoder block: bilinear x2 upsample of the concatenated [src0 | src1] low-res maps + 3x3 / pad-1 conv, as a
+// composite conv Cin -> 4*Cout on the low-res grid with a depth-to-space epilogue (conv_up.cu).
+struct UpConvParams {
+  const __nv_bfloat16* src[2];  // low-res bf16 NHWC sources in concat order, [rows, H, W, ld[s]]
+  int C[2], ld[2];              // channels taken from each source (multiples of 64; C[1] may be 0), channel strides
+  int rows, H, W;               // low-res grid; the output is [rows, 2H, 2W, out_ld]
+  int Cout;                     // output channels of the reference conv (multiple of 32); GEMM N = 4 * Cout
+  const __nv_bfloat16* w[5];    // composite weights as tcgen05 stage tiles: interior, first row, last row, first col, last col
+  const float* wc;              // corner composites, fp32 [4 corners][4 taps][Cin][4 * Cout]
+  __nv_bfloat16* out;
+  int out_ld;
+  const float* tabA;            // [rows / tab_div, Cout] epilogue tables (as ConvParams)
+  const float* tabB;
+  int tab_div;
+  int act;
+  DropCfg drop;
+};
+bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W);
+size_t conv_up_weight_elems(int Cin, int Cout);
+size_t conv_up_corner_floats(int Cin, int Cout);
+int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* w_corner, float* scratch,
+                      cudaStream_t s);
+int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
+
 int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
 // Returns 1 if the tcgen05 path took the layer, 0 if the shape is not eligible (caller falls back to the mma
 // pipeline), <0 on error.

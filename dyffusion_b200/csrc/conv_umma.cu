@@ -26,6 +26,7 @@
 #include <tuple>
 
 #include "conv.cuh"
+#include "umma.cuh"
 
 namespace dyf {
 namespace {
@@ -44,7 +45,7 @@ template <> struct Geo<S1K3> {
   static constexpr int PH = TILE_H + 2, PW = TILE_W + 2;
   static constexpr int PIX = PH * PW;               // gathered pixels
   static constexpr int SLOTS = PIX;                 // pixel slots per plane
-  static constexpr int TAPS = 9, KW = 3;
+  static constexpr int TAPS = 9, KW = 3, HALO = 2;
   static constexpr int GT = 3;                      // taps per weight stage (one filter row)
   static constexpr int SBO = PW * 16;
   __device__ static int tap_offset(int ky, int kx, int /*plane_bytes*/) { return (ky * PW + kx) * 16; }
@@ -57,7 +58,7 @@ template <> struct Geo<S1K1> {  // 1x1 convolution = plain GEMM over the 16 x 8 
   static constexpr int CH = 64, PLANES = 8, CPL = 8;
   static constexpr int PH = TILE_H, PW = TILE_W;
   static constexpr int PIX = PH * PW, SLOTS = PIX;
-  static constexpr int TAPS = 1, KW = 1, GT = 1;
+  static constexpr int TAPS = 1, KW = 1, GT = 1, HALO = 0;
   static constexpr int SBO = PW * 16;
   __device__ static int tap_offset(int, int, int) { return 0; }
   __device__ static int slot(int pr, int pc) { return pr * PW + pc; }
@@ -72,7 +73,7 @@ template <> struct Geo<S2K4> {
   static constexpr int PH = 2 * TILE_H + 2, PW = 2 * TILE_W + 2, PWH = PW / 2;
   static constexpr int PIX = PH * PW;
   static constexpr int SLOTS = PH * PWH;
-  static constexpr int TAPS = 16, KW = 4;
+  static constexpr int TAPS = 16, KW = 4, HALO = 2;
   static constexpr int GT = 4;
   static constexpr int SBO = 2 * PWH * 16;          // output row r reads patch row 2r + ky
   __device__ static int tap_offset(int ky, int kx, int plane_bytes) {
@@ -90,114 +91,6 @@ template <int MODE> struct Sizes {
   static constexpr int KSTEPS = G::CH / 16;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {  // arrive when this thread's prior cp.async land
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// One filter tap = KSTEPS back-to-back MMAs (K = 16 each) whose descriptors differ by compile-time constants; issued
-// from ONE asm block by the elected lane so that no per-MMA election / convergence code is generated.
-template <int KSTEPS, int AK, int BK>
-__device__ __forceinline__ void umma_tap(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc_first,
-                                         uint32_t leader) {
-  static_assert(KSTEPS == 2 || KSTEPS == 4, "unsupported chunk depth");
-  if constexpr (KSTEPS == 4) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pl, pa, pt;\n\t"
-        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
-        "setp.ne.b32 pl, %5, 0;\n\t"
-        "setp.ne.b32 pa, %4, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "add.u64 a1, %1, %6;\n\t add.u64 a2, a1, %6;\n\t add.u64 a3, a2, %6;\n\t"
-        "add.u64 b1, %2, %7;\n\t add.u64 b2, b1, %7;\n\t add.u64 b3, b2, %7;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t"
-        "}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_first), "r"(leader), "n"((long long)AK), "n"((long long)BK)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pl, pa, pt;\n\t"
-        ".reg .b64 a1, b1;\n\t"
-        "setp.ne.b32 pl, %5, 0;\n\t"
-        "setp.ne.b32 pa, %4, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "add.u64 a1, %1, %6;\n\t"
-        "add.u64 b1, %2, %7;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
-        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
-        "}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc_first), "r"(leader), "n"((long long)AK), "n"((long long)BK)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %1, 0;\n\t"
-      "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred;
-}
-// K-major, no-swizzle shared-memory matrix descriptor (sm_100 version bits = 1):
-//   addr(row, k16half) = start + (row % 8) * 16 + (row / 8) * SBO + k16half * LBO
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 template <int AS, int BS>
 struct __align__(8) Barriers {
   uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
@@ -210,16 +103,23 @@ struct __align__(8) Barriers {
 // TMA = true (S1K3 only): the halo patch of a chunk is ONE 4-D tensor-map copy (cp.async.bulk.tensor, box
 // 64 ch x 10 x 18 px, hardware zero fill outside the image) landing pixel-major with the 128-byte swizzle; taps are
 // still pure start-address shifts (+128 B per pixel) of a SWIZZLE_128B K-major descriptor with SBO = one patch row.
-template <int BN, int MODE, int AS, int BS, bool TMA>
+// T (TMA mode only): pixel tiles per work item, side by side along x.  All T tiles consume every weight stage before it
+// is released, so a weight byte pulled from L2 feeds T x 128 GEMM rows; the patch of the 16 x 8T super-tile is one TMA
+// box and each tile's taps are start-address shifts inside it.  GT = filter taps per weight stage.
+template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
   using S = Sizes<MODE>;
   constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
-  constexpr int A_STAGE = TMA ? ((G::PIX * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
+  static_assert(TMA || T == 1, "multi-tile work items need the TMA patch path");
+  static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
+  constexpr int PWT = TILE_W * T + G::HALO;  // patch width of the super-tile (TMA mode)
+  constexpr int PIXT = G::PH * PWT;
+  constexpr int A_STAGE = TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
   constexpr int B_TAP = BN * G::CH * 2;    // one tap of one chunk: [k8][BN rows][16 B]
-  constexpr int B_STAGE = G::GT * B_TAP;   // a weight stage carries one filter row (GT taps)
+  constexpr int B_STAGE = GT * B_TAP;      // a weight stage carries GT taps
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS * A_STAGE;
@@ -229,6 +129,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = p.Cin / G::CH;
   const int tiles_per_row = tiles_x * tiles_y;
+  // whole filter fits the weight ring and every work item uses the same n-tile: load it once, never release it
+  const bool b_resident = n_tiles == 1 && nchunks * (G::TAPS / GT) == BS;
 
   if (tid == 0) {
     for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TMA ? 1 : 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
@@ -237,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI_WARPS + 4) {  // TMEM: two accumulators of BN fp32 columns, owned by the MMA warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * T * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -253,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
     t -= row * tiles_per_row;
     const int ty = t / tiles_x;
     oy0 = ty * TILE_H;
-    ox0 = (t - ty * tiles_x) * TILE_W;
+    ox0 = (t - ty * tiles_x) * (TILE_W * T);
   };
 
   if (warp < EPI_WARPS) {
@@ -268,18 +170,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       const int acc = it & 1;
       const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
       const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
-      const int oy = oy0 + (m_local >> 3), ox = ox0 + (m_local & 7);
-      const bool valid = oy < p.Ho && ox < p.Wo;
-      const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
-      __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
-      const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+      const int oy = oy0 + (m_local >> 3);
       const float* const tA = p.tabA + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
       const float* const tB = p.tabB + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       constexpr int COLS = BN / (EPI_WARPS / 4);  // columns drained by this warp
       const int cbeg = (warp >> 2) * COLS;
+#pragma unroll 1
+      for (int tile = 0; tile < T; ++tile) {
+      const int ox = ox0 + tile * TILE_W + (m_local & 7);
+      const bool valid = oy < p.Ho && ox < p.Wo;
+      const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
+      __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
+      const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
 #pragma unroll 2
       for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
         if (n_tile * BN + c0 >= p.Cout) break;  // zero-padded output channels of a ragged last n-tile (warp-uniform)
@@ -326,6 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
           *reinterpret_cast<uint4*>(orow + c0) = pack8(y);
         }
       }
+      }
       tc_fence_before();                                    // all tcgen05.ld of this accumulator have completed
       mbar_arrive(smem_u32(&bars->acc_empty[acc]));         // hand the accumulator back to the MMA warp
     }
@@ -342,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
             const int st = ca % AS;
             mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
             const uint32_t bar = smem_u32(&bars->a_full[st]);
-            mbar_expect_tx(bar, G::PIX * 128);
+            mbar_expect_tx(bar, PIXT * 128);
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                 ::"r"(smem_u32(sA + st * A_STAGE)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * G::CH),
@@ -404,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
-      const uint32_t a_hi = TMA ? ((uint32_t)(((G::PW * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
+      const uint32_t a_hi = TMA ? ((uint32_t)(((PWT * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
                                 : ((uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14));
       const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
       const uint32_t a_lo0 = ((uint32_t)(TMA ? 1 : (PLANE >> 4)) << 16) | (smem_u32(sA) >> 4);  // LBO | start address
@@ -418,24 +324,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
         const int acc = it & 1;
         mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * BN;
+        const uint32_t tmem_acc = tmem_base + acc * T * BN;
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(bar_a_full + sa * 8, pa);
           tc_fence_after();
           const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (A_STAGE >> 4));
 #pragma unroll
-          for (int g = 0; g < G::TAPS / G::GT; ++g) {
-            mbar_wait(bar_b_full + sb * 8, pb);
-            tc_fence_after();
+          for (int g = 0; g < G::TAPS / GT; ++g) {
+            if (!b_resident || it == 0) {
+              mbar_wait(bar_b_full + sb * 8, pb);
+              tc_fence_after();
+            }
             const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_STAGE >> 4));
 #pragma unroll
-            for (int t = 0; t < G::GT; ++t) {
-              const int tap = g * G::GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
-              const int a_off = TMA ? (ky * G::PW + kx) * 128 : G::tap_offset(ky, kx, PLANE);
-              umma_tap<KSTEPS, AK, BK>(tmem_acc, a_st + (uint64_t)(a_off >> 4), b_st + (uint64_t)((t * B_TAP) >> 4), idesc,
-                                       tap ? 1u : (uint32_t)(c != 0), leader);
+            for (int t = 0; t < GT; ++t) {
+              const int tap = g * GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
+              const int a_off = TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
+#pragma unroll
+              for (int tile = 0; tile < T; ++tile)
+                umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_W * 128) >> 4),
+                                         b_st + (uint64_t)((t * B_TAP) >> 4), idesc, tap ? 1u : (uint32_t)(c != 0), leader);
             }
-            umma_commit_if(bar_b_empty + sb * 8, leader);  // weight stage free once these MMAs retire
+            if (!b_resident) umma_commit_if(bar_b_empty + sb * 8, leader);  // weight stage free once these MMAs retire
             if (++sb == BS) { sb = 0; pb ^= 1; }
           }
           umma_commit_if(bar_a_empty + sa * 8, leader);    // patch stage free
@@ -447,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   } else {
     // =============================== B producer: bulk-TMA weight tiles =============================================
     if (lane == 0) {
-      const int per_tile = nchunks * (G::TAPS / G::GT);
+      const int per_tile = nchunks * (G::TAPS / GT);
       int sb = 0, pb = 1;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int n_tile = w % n_tiles;
@@ -458,13 +368,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
           bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
           if (++sb == BS) { sb = 0; pb ^= 1; }
         }
+        if (b_resident) break;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == EPI_WARPS + 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * T * BN));
   }
 }
 
@@ -496,42 +407,29 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
   out[idx] = __float2bfloat16_rn(v);
 }
 
-template <int MODE, int BN> struct Stages;  // pipeline depths that fill the 227 KB of one SM
-template <> struct Stages<S1K3, 64> { static constexpr int A = 6, B = 3; };   // 139 KB patches +  72 KB weights
-template <> struct Stages<S1K3, 128> { static constexpr int A = 3, B = 3; };  //  70 KB patches + 144 KB weights
-template <> struct Stages<S1K1, 64> { static constexpr int A = 6, B = 4; };
-template <> struct Stages<S1K1, 128> { static constexpr int A = 6, B = 4; };
-template <> struct Stages<S2K4, 64> { static constexpr int A = 4, B = 3; };   // 157 KB patches +  48 KB weights
-template <> struct Stages<S2K4, 128> { static constexpr int A = 3, B = 3; };  // 118 KB patches +  96 KB weights
+// Pipeline shapes that fill the 227 KB of one SM.  T = pixel tiles per work item (TMA mode), GT = taps per weight stage,
+// A / B = patch / weight ring depths.
+template <int MODE, int BN, bool TMA> struct Stages;
+template <> struct Stages<S1K3, 64, true> { static constexpr int T = 2, GT = 1, A = 3, B = 9; };    // 123 KB patches +  72 KB weights
+template <> struct Stages<S1K3, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };   //  82 KB patches + 144 KB weights
+template <> struct Stages<S1K3, 64, false> { static constexpr int T = 1, GT = 3, A = 6, B = 3; };
+template <> struct Stages<S1K3, 128, false> { static constexpr int T = 1, GT = 3, A = 3, B = 3; };
+template <> struct Stages<S1K1, 64, true> { static constexpr int T = 2, GT = 1, A = 5, B = 4; };
+template <> struct Stages<S1K1, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };
+template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
+template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
+template <> struct Stages<S2K4, 64, false> { static constexpr int T = 1, GT = 4, A = 4, B = 3; };   // 157 KB patches +  48 KB weights
+template <> struct Stages<S2K4, 128, false> { static constexpr int T = 1, GT = 4, A = 3, B = 3; };  // 118 KB patches +  96 KB weights
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 4-D tensor map over a bf16 NHWC activation tensor [rows, H, W, C]: box = 64 channels x PW x PH pixels, 128-B swizzle,
-// zero fill out of bounds (= the convolution's zero padding).
+// Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
 static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return -1;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
   using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin, pw, ph};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return 0; }
-  cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi, (cuuint64_t)p.Hi, (cuuint64_t)p.rows};
-  cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Wi * p.Cin * 2, (cuuint64_t)p.Hi * p.Wi * p.Cin * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)pw, (cuuint32_t)ph, 1};
-  cuuint32_t est[4] = {1, 1, 1, 1};
   CUtensorMap m;
-  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(p.in), gdim, gstr, box, est,
-         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return -1;
+  if (make_nhwc_tmap(p.in, p.rows, p.Hi, p.Wi, p.Cin, p.Cin, pw, ph, 1, &m) != 0) return -1;
   if (cache.size() > 4096) cache.clear();
   cache[key] = m;
   *out = m;
@@ -539,20 +437,24 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
 }
 
 template <int BN, int MODE, bool TMA>
-int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap) {
+int launch_t(const ConvParams& p, cudaStream_t stream) {
   using G = Geo<MODE>;
-  constexpr int AS = TMA ? Stages<MODE, BN>::A : Stages<MODE, BN>::A, BS = Stages<MODE, BN>::B;
-  constexpr int a_stage = TMA ? ((G::PIX * 128 + 1023) / 1024) * 1024 : Sizes<MODE>::A_STAGE;
-  constexpr int smem = AS * a_stage + BS * G::GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
+  using St = Stages<MODE, BN, TMA>;
+  constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
+  constexpr int a_stage = TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE>::A_STAGE;
+  constexpr int smem = AS * a_stage + BS * GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(2 * T * BN <= 512, "TMEM budget exceeded");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     DYF_CUDA_OK(cudaGetDevice(&dev));
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W, tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
+  CUtensorMap tmap{};
+  if (TMA && make_patch_tmap(p, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
+  const int tiles_x = (p.Wo + TILE_W * T - 1) / (TILE_W * T), tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
   const int n_tiles = (p.Cout + BN - 1) / BN;
   const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
   if (work > 0x7fffffffLL) { set_error("conv_umma: too many tiles"); return -1; }
@@ -560,8 +462,8 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap& tmap) 
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_umma_kernel<BN, MODE, AS, BS, TMA><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work,
-                                                                        tmap);
+  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
+                                                                                (int)work, tmap);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -594,24 +496,26 @@ bool conv_umma_eligible(const ConvParams& p) {
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
   const bool n64 = umma_tile_n(p.Cout) == 64;
-  static const CUtensorMap dummy{};
   const int mode = mode_of(p.KH, p.stride, p.pad);
   static const char* env_a = getenv("DYF_UMMA_A");  // "cpasync" forces the cp.async patch gather
   const bool want_tma = !(env_a && env_a[0] == 'c');
-  CUtensorMap tm;
   // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
   //  and UMMA reads alike -- verified on hardware)
   if (mode == S1K3) {
-    if (want_tma && make_patch_tmap(p, Geo<S1K3>::PW, Geo<S1K3>::PH, &tm) == 0)
-      return n64 ? launch_t<64, S1K3, true>(p, stream, tm) : launch_t<128, S1K3, true>(p, stream, tm);
-    return n64 ? launch_t<64, S1K3, false>(p, stream, dummy) : launch_t<128, S1K3, false>(p, stream, dummy);
+    if (want_tma) {
+      const int rc = n64 ? launch_t<64, S1K3, true>(p, stream) : launch_t<128, S1K3, true>(p, stream);
+      if (rc != 0) return rc;
+    }
+    return n64 ? launch_t<64, S1K3, false>(p, stream) : launch_t<128, S1K3, false>(p, stream);
   }
   if (mode == S1K1) {
-    if (want_tma && make_patch_tmap(p, Geo<S1K1>::PW, Geo<S1K1>::PH, &tm) == 0)
-      return n64 ? launch_t<64, S1K1, true>(p, stream, tm) : launch_t<128, S1K1, true>(p, stream, tm);
-    return n64 ? launch_t<64, S1K1, false>(p, stream, dummy) : launch_t<128, S1K1, false>(p, stream, dummy);
+    if (want_tma) {
+      const int rc = n64 ? launch_t<64, S1K1, true>(p, stream) : launch_t<128, S1K1, true>(p, stream);
+      if (rc != 0) return rc;
+    }
+    return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
   }
-  return n64 ? launch_t<64, S2K4, false>(p, stream, dummy) : launch_t<128, S2K4, false>(p, stream, dummy);
+  return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
 }
 
 int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,

@@ -1,0 +1,492 @@
+// Decoder block of the Navier-Stokes backbone as ONE tensor-core kernel: bilinear x2 upsample (align_corners=False) of
+// the concatenated [x, skip] maps followed by the 3x3 / pad-1 convolution (reference: src/models/unet_simple.py:41-51,
+// :133-140), without ever materialising the upsampled tensor.
+//
+// Algebra.  Bilinear x2 is a fixed separable stencil, u[2i] = .25 x[i-1] + .75 x[i], u[2i+1] = .75 x[i] + .25 x[i+1]
+// (indices clamped), so a 3x3 conv over u is, per output parity class (a, b) = (row & 1, col & 1), a 3x3 conv over the
+// LOW-resolution map x with composite weights  Wc[a,b][di,dj] = sum_{ky,kx} V_a[di,ky] H_b[dj,kx] w[ky,kx].
+// Stacking the four classes along the GEMM N axis turns the block into a plain 3x3 conv Cin -> 4*Cout on the low-res
+// grid whose epilogue stores depth-to-space: same FLOPs as the reference's conv, a quarter of its activation traffic,
+// N = 128 tiles even for the Cout = 64 layer, and no upsample kernel.
+//
+// Borders.  The reference zero-pads the UPSAMPLED map and clamps the interpolation; on the first/last low-res row or
+// column this gives different 1-D maps (V_top, V_bottom, H_left, H_right -- computed on the host by simulating the
+// stencil), i.e. the border pixels are the same conv with other weights.  They are therefore computed by their own
+// tiles: ROW tiles (1 x 128 pixels of the first/last row), COL tiles (128 x 1), and the four corners per image by a
+// small CUDA-core kernel; MAIN tiles skip the border ring.  Every output pixel is written exactly once.
+//
+// Pipeline = conv_umma.cu's: persistent CTAs, TMA box loads of the low-res patch (zero fill = the low-res taps that
+// fall outside the image, whose composite weights are irrelevant), weights by bulk TMA, tcgen05.mma into two
+// ping-pong TMEM accumulator sets, 8 epilogue warps.
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace dyf {
+namespace {
+
+constexpr int BN = 128;                                  // GEMM N tile (columns of 4*Cout)
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 1 + 1 + 1) * 32;    // epilogue + A producer + MMA + weight producer warps
+constexpr int B_TAP = BN * 64 * 2;                       // one tap of one 64-channel chunk: [k8][BN][8] bf16
+
+enum Kind { K_MAIN = 0, K_ROW = 1, K_COL = 2 };
+
+template <int KIND> struct UGeo;
+template <> struct UGeo<K_MAIN> {  // 16 x 16 low-res pixels = two 16 x 8 M-tiles sharing every weight stage
+  static constexpr int T = 2, NBOX = 1, BW = 18, BH = 18;
+  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = REGION;
+  static constexpr int SBO = BW * 128, AS = 2, BS = 8;
+  __device__ static constexpr int tap_off(int ty, int tx) { return (ty * BW + tx) * 128; }
+};
+template <> struct UGeo<K_ROW> {   // 128 consecutive pixels of the first / last low-res row
+  static constexpr int T = 1, NBOX = 1, BW = 130, BH = 3;
+  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = REGION;
+  static constexpr int SBO = 1024, AS = 2, BS = 7;
+  __device__ static constexpr int tap_off(int ty, int tx) { return (ty * BW + tx) * 128; }
+};
+template <> struct UGeo<K_COL> {   // 128 consecutive pixels of the first / last low-res column: one box per tap column
+  static constexpr int T = 1, NBOX = 3, BW = 1, BH = 130;
+  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = NBOX * REGION;
+  static constexpr int SBO = 1024, AS = 2, BS = 7;
+  __device__ static constexpr int tap_off(int ty, int tx) { return tx * REGION + ty * 128; }
+};
+
+template <int AS, int BS>
+struct __align__(8) UBarriers {
+  uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+// Fused epilogue of 8 consecutive GEMM columns (one parity class, channels co..co+7) of low-res pixel (i, j).
+__device__ __forceinline__ void up_store8(const UpConvParams& p, int img, int i, int j, int n, float* y) {
+  const int cls = n / p.Cout, co = n - cls * p.Cout;
+  const int oy = 2 * i + (cls >> 1), ox = 2 * j + (cls & 1);
+  const float* const tA = p.tabA + (size_t)(img / p.tab_div) * p.Cout + co;
+  const float* const tB = p.tabB + (size_t)(img / p.tab_div) * p.Cout + co;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(tA)), a1 = __ldg(reinterpret_cast<const float4*>(tA) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(tB)), b1 = __ldg(reinterpret_cast<const float4*>(tB) + 1);
+  y[0] = fmaf(y[0], a0.x, b0.x); y[1] = fmaf(y[1], a0.y, b0.y); y[2] = fmaf(y[2], a0.z, b0.z); y[3] = fmaf(y[3], a0.w, b0.w);
+  y[4] = fmaf(y[4], a1.x, b1.x); y[5] = fmaf(y[5], a1.y, b1.y); y[6] = fmaf(y[6], a1.z, b1.z); y[7] = fmaf(y[7], a1.w, b1.w);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = apply_act(y[e], p.act);
+  const long long m = ((long long)img * (2 * p.H) + oy) * (2 * p.W) + ox;  // hi-res pixel index (dropout element order)
+  if (p.drop.thresh) {
+    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + co);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = ((keep >> e) & 1u) ? y[e] * p.drop.scale : 0.f;
+  }
+  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.out_ld + co) = pack8(y);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams p, int tiles_a, int n_tiles, int num_work,
+                                                             const __grid_constant__ CUtensorMap tmap0,
+                                                             const __grid_constant__ CUtensorMap tmap1) {
+  using G = UGeo<KIND>;
+  constexpr int AS = G::AS, BS = G::BS, T = G::T, A_STAGE = G::A_STAGE;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AS * A_STAGE;
+  using Bars = UBarriers<AS, BS>;
+  Bars* bars = reinterpret_cast<Bars*>(sB + BS * B_TAP);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nch0 = p.C[0] >> 6, nchunks = (p.C[0] + p.C[1]) >> 6;
+
+  if (tid == 0) {
+    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * T * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // work item -> (n_tile, image, side | tile origin).  MAIN: tiles_a = tiles_x (16-pixel blocks per row); ROW / COL:
+  // tiles_a = 128-pixel blocks along the border, `side` 0 = first row / column, 1 = last.
+  auto decode = [&](int w, int& n_tile, int& img, int& i0, int& j0, int& side) {
+    n_tile = w % n_tiles;
+    int t = w / n_tiles;
+    if constexpr (KIND == K_MAIN) {
+      const int tiles_y = (p.H + 15) >> 4, per_img = tiles_a * tiles_y;
+      img = t / per_img;
+      t -= img * per_img;
+      const int ty = t / tiles_a;
+      i0 = ty * 16;
+      j0 = (t - ty * tiles_a) * 16;
+      side = 0;
+    } else {
+      const int per_img = 2 * tiles_a;
+      img = t / per_img;
+      t -= img * per_img;
+      side = t / tiles_a;
+      const int blk = (t - side * tiles_a) * 128;
+      if constexpr (KIND == K_ROW) { i0 = side ? p.H - 1 : 0; j0 = blk; }
+      else { j0 = side ? p.W - 1 : 0; i0 = blk; }
+    }
+  };
+
+  if (warp < EPI_WARPS) {
+    // =============================== epilogue: TMEM -> affine/activation/dropout -> depth-to-space stores ==========
+    int it = 0;
+    const int quarter = warp & 3, m_local = quarter * 32 + lane;
+    constexpr int COLS = BN / (EPI_WARPS / 4);
+    const int cbeg = (warp >> 2) * COLS;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      int n_tile, img, i0, j0, side;
+      decode(w, n_tile, img, i0, j0, side);
+      const int acc = it & 1;
+      mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tile = 0; tile < T; ++tile) {
+        int i, j;
+        bool valid;
+        if constexpr (KIND == K_MAIN) {
+          i = i0 + (m_local >> 3); j = j0 + tile * 8 + (m_local & 7);
+          valid = i >= 1 && i <= p.H - 2 && j >= 1 && j <= p.W - 2;
+        } else if constexpr (KIND == K_ROW) {
+          i = i0; j = j0 + m_local;
+          valid = j >= 1 && j <= p.W - 2;
+        } else {
+          j = j0; i = i0 + m_local;
+          valid = i >= 1 && i <= p.H - 2;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
+#pragma unroll 2
+        for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(taddr + c0, v);
+          if (valid) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[e]);
+            up_store8(p, img, i, j, n_tile * BN + c0, y);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+    }
+  } else if (warp == EPI_WARPS) {
+    // =============================== A producer: TMA boxes of the low-res [x | skip] patch =========================
+    if (lane == 0) {
+      int ca = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int n_tile, img, i0, j0, side;
+        decode(w, n_tile, img, i0, j0, side);
+        for (int c = 0; c < nchunks; ++c, ++ca) {
+          const int st = ca % AS;
+          mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&bars->a_full[st]);
+          mbar_expect_tx(bar, G::NBOX * G::BW * G::BH * 128);
+          const uint64_t tm = reinterpret_cast<uint64_t>(c < nch0 ? &tmap0 : &tmap1);
+          const int cc = (c < nch0 ? c : c - nch0) * 64;
+#pragma unroll
+          for (int b = 0; b < G::NBOX; ++b) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                ::"r"(smem_u32(sA + st * A_STAGE + b * G::REGION)), "l"(tm), "r"(cc), "r"(j0 - 1 + b), "r"(i0 - 1), "r"(img),
+                  "r"(bar) : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // =============================== MMA issuer ====================================================================
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = (uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+    const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
+    const uint32_t a_lo0 = (1u << 16) | (smem_u32(sA) >> 4);
+    const uint32_t b_lo0 = ((uint32_t)((BN * 16) >> 4) << 16) | (smem_u32(sB) >> 4);
+    const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
+    const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+    constexpr int AK = 32 >> 4, BK = (2 * BN * 16) >> 4;
+    int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * T * BN;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar_a_full + sa * 8, pa);
+        tc_fence_after();
+        const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (A_STAGE >> 4));
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(bar_b_full + sb * 8, pb);
+          tc_fence_after();
+          const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_TAP >> 4));
+          const int a_off = G::tap_off(tap / 3, tap % 3);
+#pragma unroll
+          for (int tile = 0; tile < T; ++tile)
+            umma_tap<4, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * 8 * 128) >> 4), b_st, idesc,
+                                tap ? 1u : (uint32_t)(c != 0), leader);
+          umma_commit_if(bar_b_empty + sb * 8, leader);
+          if (++sb == BS) { sb = 0; pb ^= 1; }
+        }
+        umma_commit_if(bar_a_empty + sa * 8, leader);
+        if (++sa == AS) { sa = 0; pa ^= 1; }
+      }
+      umma_commit_if(smem_u32(&bars->acc_full[acc]), leader);
+    }
+  } else {
+    // =============================== B producer: one bulk-TMA copy per (chunk, tap) weight tile ====================
+    if (lane == 0) {
+      const int per_tile = nchunks * 9;
+      int sb = 0, pb = 1;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int n_tile, img, i0, j0, side;
+        decode(w, n_tile, img, i0, j0, side);
+        const __nv_bfloat16* wv = KIND == K_MAIN ? p.w[0] : KIND == K_ROW ? p.w[1 + side] : p.w[3 + side];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wv) + (size_t)n_tile * per_tile * B_TAP;
+        for (int i = 0; i < per_tile; ++i) {
+          mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
+          mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_TAP);
+          bulk_g2s(smem_u32(sB + sb * B_TAP), src + (size_t)i * B_TAP, B_TAP, smem_u32(&bars->b_full[sb]));
+          if (++sb == BS) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * T * BN));
+  }
+}
+
+// The four corner pixels of every image (2 x 2 in-bounds taps each): CUDA cores, fp32 composite weights
+// wc[corner][tap][Cin][4*Cout].  One block = one corner x 8 images x 256 GEMM columns: lanes own 8 consecutive columns
+// (coalesced weight rows), the 8 warps split the 4*Cin reduction and combine through shared memory in a fixed order.
+constexpr int CORNER_IMGS = 8;
+__global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams p) {
+  extern __shared__ float sx[];  // [img][tap][Cin] inputs, then [slice][img][lane][8] partial sums
+  const int corner = blockIdx.x, img0 = blockIdx.y * CORNER_IMGS;
+  const int Cin = p.C[0] + p.C[1], N = 4 * p.Cout, K = 4 * Cin;
+  const int bottom = corner >> 1, right = corner & 1;
+  const int i = bottom ? p.H - 1 : 0, j = right ? p.W - 1 : 0;
+  const int nimg = min(CORNER_IMGS, p.rows - img0);
+  for (int e = threadIdx.x; e < CORNER_IMGS * K; e += blockDim.x) {
+    const int c = e % Cin, t = (e / Cin) & 3, im = e / K;
+    const int ii = i + (t >> 1) - bottom, jj = j + (t & 1) - right;  // taps (di, dj) in {0,1}^2 (top/left) or {-1,0}^2
+    const int s = c < p.C[0] ? 0 : 1, cs = s ? c - p.C[0] : c;
+    sx[e] = im < nimg ? __bfloat162float(p.src[s][(((size_t)(img0 + im) * p.H + ii) * p.W + jj) * p.ld[s] + cs]) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n0 = (blockIdx.z * 32 + lane) * 8;
+  float* red = sx + CORNER_IMGS * K;
+  float acc[CORNER_IMGS][8];
+#pragma unroll
+  for (int im = 0; im < CORNER_IMGS; ++im)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[im][e] = 0.f;
+  if (n0 < N) {
+    const float* wc = p.wc + (size_t)corner * K * N + n0;
+    const int per = K / 8;
+#pragma unroll 4
+    for (int tc = slice * per; tc < (slice + 1) * per; ++tc) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N) + 1);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int im = 0; im < CORNER_IMGS; ++im) {
+        const float x = sx[im * K + tc];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[im][e] = fmaf(x, wv[e], acc[im][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int im = 0; im < CORNER_IMGS; ++im)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[((slice * CORNER_IMGS + im) * 32 + lane) * 8 + e] = acc[im][e];
+  __syncthreads();
+  const int im = slice;  // warp `slice` finishes image `slice`
+  if (n0 < N && im < nimg) {
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) v += red[((sl * CORNER_IMGS + im) * 32 + lane) * 8 + e];
+      y[e] = v;
+    }
+    up_store8(p, img0 + im, i, j, n0, y);
+  }
+}
+
+// Composite weights of one border variant: out[n = cls*Cout + co][ci][di][dj] = sum V[a][di][ky] H[b][dj][kx] w[co][ci][ky][kx]
+struct Maps { float V[2][3][3], H[2][3][3]; };
+__global__ void __launch_bounds__(256) compose_up_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout,
+                                                        int Cin, Maps m) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)4 * Cout * Cin) return;
+  const int ci = (int)(idx % Cin), n = (int)(idx / Cin);
+  const int cls = n / Cout, co = n - cls * Cout, a = cls >> 1, b = cls & 1;
+  float k[3][3];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) k[t / 3][t % 3] = w[((size_t)co * Cin + ci) * 9 + t];
+#pragma unroll
+  for (int di = 0; di < 3; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) {
+      float s = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) s = fmaf(m.V[a][di][ky] * m.H[b][dj][kx], k[ky][kx], s);
+      out[((size_t)n * Cin + ci) * 9 + di * 3 + dj] = s;
+    }
+}
+// corner layout: wc[tap = tdi*2 + tdj][ci][n] from a composed variant [n][ci][3][3]; (di, dj) = (tdi, tdj) - (bottom, right)
+__global__ void __launch_bounds__(256) corner_layout_kernel(const float* __restrict__ comp, float* __restrict__ wc, int N,
+                                                           int Cin, int bottom, int right) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)4 * Cin * N) return;
+  const int n = (int)(idx % N), ci = (int)((idx / N) % Cin), t = (int)(idx / ((long long)N * Cin));
+  const int di = (t >> 1) - bottom + 1, dj = (t & 1) - right + 1;  // index into the 3 x 3 composite taps
+  wc[idx] = comp[((size_t)n * Cin + ci) * 9 + di * 3 + dj];
+}
+
+// 1-D composite maps by simulating the reference ops on basis vectors: M[a][d][k] = coefficient of w[k] * x[i + d - 1]
+// in output 2i + a of (zero-padded 3-tap conv) o (clamped bilinear x2), for i at the start / interior / end of the axis.
+void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
+  const int L = 5, i = where == 0 ? 0 : where == 1 ? 2 : L - 1;
+  for (int a = 0; a < 2; ++a)
+    for (int d = 0; d < 3; ++d)
+      for (int k = 0; k < 3; ++k) {
+        const int src = i + d - 1, r = 2 * i + a + k - 1;  // source pixel, upsampled position read by tap k
+        double v = 0.0;
+        if (src >= 0 && src < L && r >= 0 && r < 2 * L) {
+          const int q = r >> 1;
+          const int lo = r & 1 ? q : (q > 0 ? q - 1 : 0), hi = r & 1 ? (q + 1 < L ? q + 1 : L - 1) : q;
+          const double wlo = r & 1 ? 0.75 : 0.25, whi = 1.0 - wlo;
+          v = (lo == src ? wlo : 0.0) + (hi == src ? whi : 0.0);
+        }
+        M[a][d][k] = (float)v;
+      }
+}
+
+template <int KIND>
+int launch_kind(const UpConvParams& p, cudaStream_t stream) {
+  using G = UGeo<KIND>;
+  constexpr int smem = G::AS * G::A_STAGE + G::BS * B_TAP + (int)sizeof(UBarriers<G::AS, G::BS>) + 64;
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DYF_CUDA_OK(cudaGetDevice(&dev));
+    DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  using Key = std::tuple<const void*, int, int, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  CUtensorMap tm[2];
+  for (int s = 0; s < 2; ++s) {
+    const int sidx = p.C[s] ? s : 0;  // single-source layers: the second map is never used
+    const Key key{p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], KIND};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      CUtensorMap m;
+      if (make_nhwc_tmap(p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], G::BW, G::BH, 1, &m) != 0) {
+        set_error("conv_up: cuTensorMapEncodeTiled failed");
+        return -1;
+      }
+      if (cache.size() > 4096) cache.clear();
+      it = cache.emplace(key, m).first;
+    }
+    tm[s] = it->second;
+  }
+  const int n_tiles = 4 * p.Cout / BN;
+  const int tiles_a = KIND == K_MAIN ? (p.W + 15) / 16 : KIND == K_ROW ? (p.W + 127) / 128 : (p.H + 127) / 128;
+  const long long work = KIND == K_MAIN ? (long long)tiles_a * ((p.H + 15) / 16) * p.rows * n_tiles
+                                        : (long long)2 * tiles_a * p.rows * n_tiles;
+  if (work > 0x7fffffffLL) { set_error("conv_up: too many tiles"); return -1; }
+  const int grid = (int)(work < num_sms ? work : num_sms);
+  const int Cin = p.C[0] + p.C[1];
+  // algorithmic FLOPs of the reference's conv are booked on the MAIN launch (border launches recompute ring pixels)
+  const double flops = KIND == K_MAIN ? 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin : 0.0;
+  const double bytes = KIND == K_MAIN ? 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin) : 0.0;
+  ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
+  conv_up_kernel<KIND><<<grid, THREADS, smem, stream>>>(p, tiles_a, n_tiles, (int)work, tm[0], tm[1]);
+  DYF_LAUNCH_OK("conv_up_kernel");
+  return 0;
+}
+
+}  // namespace
+
+bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W) {
+  return C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 32 == 0 && H >= 16 && W >= 16;
+}
+size_t conv_up_weight_elems(int Cin, int Cout) { return (size_t)4 * Cout * Cin * 9; }      // per UMMA variant (bf16)
+size_t conv_up_corner_floats(int Cin, int Cout) { return (size_t)4 * 4 * Cin * 4 * Cout; }  // all four corners (fp32)
+
+// w: conv weight fp32 [Cout, Cin, 3, 3].  Fills the five UMMA variants (interior, top, bottom, left, right) and the
+// corner table.  `scratch` must hold 4*Cout*Cin*9 floats.
+int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* w_corner, float* scratch,
+                      cudaStream_t s) {
+  float ax[3][2][3][3];
+  for (int k = 0; k < 3; ++k) axis_maps(k, ax[k]);
+  const long long total = (long long)4 * Cout * Cin;
+  auto compose = [&](int vk, int hk) {
+    Maps m;
+    memcpy(m.V, ax[vk], sizeof(m.V));
+    memcpy(m.H, ax[hk], sizeof(m.H));
+    compose_up_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, scratch, Cout, Cin, m);
+  };
+  const int vks[5] = {1, 0, 2, 1, 1}, hks[5] = {1, 1, 1, 0, 2};
+  for (int v = 0; v < 5; ++v) {
+    compose(vks[v], hks[v]);
+    DYF_LAUNCH_OK("compose_up_kernel");
+    int rc = launch_repack_umma(scratch, w_variants[v], 4 * Cout, Cin, 3, 1, 1, 0, s);
+    if (rc) return rc;
+  }
+  const int N = 4 * Cout;
+  for (int corner = 0; corner < 4; ++corner) {
+    const int bottom = corner >> 1, right = corner & 1;
+    compose(bottom ? 2 : 0, right ? 2 : 0);
+    DYF_LAUNCH_OK("compose_up_kernel");
+    corner_layout_kernel<<<cdiv((long long)4 * Cin * N, 256), 256, 0, s>>>(scratch, w_corner + (size_t)corner * 4 * Cin * N, N,
+                                                                         Cin, bottom, right);
+    DYF_LAUNCH_OK("corner_layout_kernel");
+  }
+  return 0;
+}
+
+int launch_conv_up(const UpConvParams& p, cudaStream_t stream) {
+  if (!conv_up_shape_ok(p.C[0], p.C[1], p.Cout, p.H, p.W) || (p.out_ld & 7) || (p.ld[0] & 7) || (p.C[1] && (p.ld[1] & 7))) {
+    set_error("conv_up: unsupported shape");
+    return -1;
+  }
+  int rc = launch_kind<K_MAIN>(p, stream);
+  if (!rc) rc = launch_kind<K_ROW>(p, stream);
+  if (!rc) rc = launch_kind<K_COL>(p, stream);
+  if (rc) return rc;
+  const int Cin = p.C[0] + p.C[1];
+  const size_t smem = ((size_t)CORNER_IMGS * 4 * Cin + 8 * CORNER_IMGS * 32 * 8) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_corner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid(4, cdiv(p.rows, CORNER_IMGS), cdiv(4 * p.Cout, 32 * 8));
+  ProfScope prof(stream, KC_CONV_UMMA);
+  conv_up_corner_kernel<<<grid, 256, smem, stream>>>(p);
+  DYF_LAUNCH_OK("conv_up_corner_kernel");
+  return 0;
+}
+
+}  // namespace dyf

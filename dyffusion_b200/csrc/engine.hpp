@@ -33,6 +33,8 @@ struct ConvLayer {
   int flops_cin = 0;                            // channels to count per tap in FLOP accounting (0 = Cin)
   int comp_wi = -1, comp_bi = -1, comp_cm = 0;  // composite layer: preceded by a folded 1x1 conv (weights, bias, width)
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
+  long long up_off[5] = {-1, -1, -1, -1, -1}; // fused upsample+conv: composite weight variants in Net::wq_umma
+  long long upc_off = -1;                     //   ... and the corner composites in Net::w_corner (floats)
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
   int table = -1;                             // index into Net::time_layers
 };
@@ -44,7 +46,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
 constexpr int BUF_NONE = -1;
 
 struct Op {
@@ -88,6 +90,8 @@ struct Net {
   float* packed = nullptr;             // device: all fp32 params + folded vectors
   __nv_bfloat16* wq = nullptr;         // device: packed bf16 conv weights
   __nv_bfloat16* wq_umma = nullptr;    // device: weights of tcgen05-eligible layers as UMMA stage tiles
+  float* w_corner = nullptr;           // device: corner composites of the fused upsample+conv layers
+  size_t wc_floats = 0;
   TimeLayer* d_time_layers = nullptr;  // device copy
   bool finalized = false;
   int Hin = 0, Win = 0;                // network grid (after the optional outer resize)

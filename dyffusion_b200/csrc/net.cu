@@ -14,6 +14,7 @@ Net::~Net() {
   if (packed) cudaFree(packed);
   if (wq) cudaFree(wq);
   if (wq_umma) cudaFree(wq_umma);
+  if (w_corner) cudaFree(w_corner);
   if (d_time_layers) cudaFree(d_time_layers);
 }
 
@@ -244,16 +245,31 @@ int Net::build_unet_simple() {
     const int skip = i > 0 ? skips[5 - i] : BUF_NONE;
     const int c0 = bufs[x].C, c1 = skip >= 0 ? bufs[skip].C : 0;
     H *= 2; W *= 2;
-    int up = add_buf(H, W, c0 + c1);
-    Op u{}; u.type = OP_UPSAMPLE; u.in0 = x; u.in1 = skip; u.out = up; u.c0 = c0; u.c1 = c1; u.scale = 2; u.bilinear = 1;
-    ops.push_back(u);
+    // 3x3 decoder blocks on large grids run as ONE kernel: upsample + concat + conv as a composite conv on the low-res
+    // grid (conv_up.cu).  Small grids keep the two-kernel path (their border tiles would dominate).
+    const char* env_min = getenv("DYF_UPFUSE_MIN");  // smallest upsampled grid side that takes the fused kernel
+    const int fuse_min = env_min ? atoi(env_min) : 128;
+    const bool fuse_up = dec_k[i] == 3 && std::min(H, W) >= fuse_min && conv_up_shape_ok(c0, c1, dec_out[i], H / 2, W / 2) &&
+                         !getenv("DYF_DISABLE_UPFUSE");
+    int up = BUF_NONE;
+    if (!fuse_up) {
+      up = add_buf(H, W, c0 + c1);
+      Op u{}; u.type = OP_UPSAMPLE; u.in0 = x; u.in1 = skip; u.out = up; u.c0 = c0; u.c1 = c1; u.scale = 2; u.bilinear = 1;
+      ops.push_back(u);
+    }
     int tw = -1, tb = -1;
     attach_time(tw, tb, p + ".time_mlp.1", dec_out[i]);
     int li = add_conv(p + ".ops.1", c0 + c1, dec_out[i], dec_k[i], 1, dec_p[i]);
     attach_bn(convs[li], p + ".ops.2");
     convs[li].tw = tw; convs[li].tb = tb;
     int y = add_buf(H, W, dec_out[i]);
-    Op o{}; o.type = OP_CONV; o.in0 = up; o.out = y; o.layer = li; o.act = ACT_RELU; o.drop_p = d.dropout; o.site = site++;
+    Op o{}; o.type = fuse_up ? OP_CONV_UP : OP_CONV; o.in0 = fuse_up ? x : up; o.in1 = fuse_up ? skip : BUF_NONE; o.out = y;
+    o.c0 = c0; o.c1 = c1; o.layer = li; o.act = ACT_RELU; o.drop_p = d.dropout; o.site = site++;
+    if (fuse_up) {
+      for (int v = 0; v < 5; ++v) { convs[li].up_off[v] = (long long)wu_elems; wu_elems += conv_up_weight_elems(c0 + c1, dec_out[i]); }
+      convs[li].upc_off = (long long)wc_floats;
+      wc_floats += conv_up_corner_floats(c0 + c1, dec_out[i]);
+    }
     ops.push_back(o);
     x = y;
   }
@@ -492,7 +508,18 @@ int Net::finalize(cudaStream_t s) {
     if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
   if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
   if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
+  if (!w_corner && wc_floats) DYF_CUDA_OK(cudaMalloc(&w_corner, wc_floats * sizeof(float)));
   for (auto& c : convs) {
+    if (c.upc_off >= 0) {  // fused upsample + conv: composite weight variants (conv_up.cu)
+      float* scratch = nullptr;
+      DYF_CUDA_OK(cudaMalloc(&scratch, conv_up_weight_elems(c.Cin, c.Cout) * sizeof(float)));
+      __nv_bfloat16* variants[5];
+      for (int v = 0; v < 5; ++v) variants[v] = wq_umma + c.up_off[v];
+      int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, w_corner + c.upc_off, scratch, s);
+      if (ru) return ru;
+      DYF_CUDA_OK(cudaStreamSynchronize(s));
+      DYF_CUDA_OK(cudaFree(scratch));
+    }
     if (c.convt_z) {  // ConvTranspose2d weight re-laid out as a 1x1 conv weight [16 * Cout_t, Cin] (fp32 staging)
       float* wz = nullptr;
       DYF_CUDA_OK(cudaMalloc(&wz, (size_t)c.Cout * c.Cin * sizeof(float)));
@@ -660,6 +687,22 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         rc = launch_conv_umma(p, s);
         if (rc == 0) rc = launch_conv_mma(p, s);
         else if (rc > 0) rc = 0;
+        break;
+      }
+      case OP_CONV_UP: {
+        const ConvLayer& c = convs[o.layer];
+        UpConvParams p{};
+        p.src[0] = bp[o.in0]; p.C[0] = o.c0; p.ld[0] = bufs[o.in0].C;
+        p.src[1] = o.in1 >= 0 ? bp[o.in1] : bp[o.in0]; p.C[1] = o.c1; p.ld[1] = o.in1 >= 0 ? bufs[o.in1].C : bufs[o.in0].C;
+        p.rows = rows; p.H = bufs[o.in0].H; p.W = bufs[o.in0].W; p.Cout = c.Cout;
+        for (int v = 0; v < 5; ++v) p.w[v] = wq_umma + c.up_off[v];
+        p.wc = w_corner + c.upc_off;
+        p.out = bp[o.out]; p.out_ld = bufs[o.out].C;
+        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.tab_div = group_rows; p.act = o.act;
+        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        rc = launch_conv_up(p, s);
         break;
       }
       case OP_UPSAMPLE: {
