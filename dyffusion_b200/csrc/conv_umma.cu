@@ -37,8 +37,8 @@ constexpr int THREADS = (EPI_WARPS + 4 + 2) * 32;  // epilogue + 4 producer warp
 
 enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2 };
 
-template <int MODE> struct Geo;
-template <> struct Geo<S1K3> {
+template <int MODE, int T = 1> struct Geo;  // T = pixel tiles side by side per work item (gathered patches: stride-2 mode only)
+template <int T> struct Geo<S1K3, T> {
   static constexpr int CH = 64;                     // channels per chunk
   static constexpr int PLANES = 8;                  // 16-byte planes per chunk
   static constexpr int CPL = 8;                     // 8-channel groups per pixel in a chunk
@@ -54,7 +54,7 @@ template <> struct Geo<S1K3> {
   __device__ static int in_y(int oy0, int pr) { return oy0 - 1 + pr; }
   __device__ static int in_x(int ox0, int pc) { return ox0 - 1 + pc; }
 };
-template <> struct Geo<S1K1> {  // 1x1 convolution = plain GEMM over the 16 x 8 pixel tile (no halo, one "tap")
+template <int T> struct Geo<S1K1, T> {  // 1x1 convolution = plain GEMM over the 16 x 8 pixel tile (no halo, one "tap")
   static constexpr int CH = 64, PLANES = 8, CPL = 8;
   static constexpr int PH = TILE_H, PW = TILE_W;
   static constexpr int PIX = PH * PW, SLOTS = PIX;
@@ -66,11 +66,11 @@ template <> struct Geo<S1K1> {  // 1x1 convolution = plain GEMM over the 16 x 8 
   __device__ static int in_y(int oy0, int pr) { return oy0 + pr; }
   __device__ static int in_x(int ox0, int pc) { return ox0 + pc; }
 };
-template <> struct Geo<S2K4> {
+template <int T> struct Geo<S2K4, T> {
   static constexpr int CH = 32;
   static constexpr int PLANES = 8;                  // 2 column parities x 4 channel groups
   static constexpr int CPL = 4;
-  static constexpr int PH = 2 * TILE_H + 2, PW = 2 * TILE_W + 2, PWH = PW / 2;
+  static constexpr int PH = 2 * TILE_H + 2, PW = 2 * TILE_W * T + 2, PWH = PW / 2;
   static constexpr int PIX = PH * PW;
   static constexpr int SLOTS = PH * PWH;
   static constexpr int TAPS = 16, KW = 4, HALO = 2;
@@ -84,8 +84,8 @@ template <> struct Geo<S2K4> {
   __device__ static int in_y(int oy0, int pr) { return 2 * oy0 - 1 + pr; }
   __device__ static int in_x(int ox0, int pc) { return 2 * ox0 - 1 + pc; }
 };
-template <int MODE> struct Sizes {
-  using G = Geo<MODE>;
+template <int MODE, int T = 1> struct Sizes {
+  using G = Geo<MODE, T>;
   static constexpr int PLANE = (G::SLOTS | 1) * 16;  // odd slot pitch => conflict-free 16-byte fills across planes
   static constexpr int A_STAGE = G::PLANES * PLANE;
   static constexpr int KSTEPS = G::CH / 16;
@@ -110,10 +110,10 @@ template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap) {
-  using G = Geo<MODE>;
-  using S = Sizes<MODE>;
+  using G = Geo<MODE, TMA ? 1 : T>;
+  using S = Sizes<MODE, TMA ? 1 : T>;
   constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
-  static_assert(TMA || T == 1, "multi-tile work items need the TMA patch path");
+  static_assert(TMA || T == 1 || MODE == S2K4, "multi-tile gathered patches: stride-2 mode only");
   static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
   constexpr int PWT = TILE_W * T + G::HALO;  // patch width of the super-tile (TMA mode)
   constexpr int PIXT = G::PH * PWT;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   uint8_t* sB = smem + AS * A_STAGE;
   using Bars = Barriers<AS, BS>;
   Bars* bars = reinterpret_cast<Bars*>(sB + BS * B_STAGE);
+  float* sTab = reinterpret_cast<float*>(sB + BS * B_STAGE + ((sizeof(Bars) + 15) & ~15));  // [2 acc][A | B][BN] epilogue tables
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = p.Cin / G::CH;
@@ -171,8 +172,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
       const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
       const int oy = oy0 + (m_local >> 3);
-      const float* const tA = p.tabA + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
-      const float* const tB = p.tabB + (size_t)(row / p.tab_div) * p.Cout + n_tile * BN;
+      // stage this item's epilogue tables in shared memory (one global round trip per item instead of one per 8 columns)
+      float* const tA = sTab + acc * 2 * BN;
+      float* const tB = tA + BN;
+      if (tid < BN) {
+        const int col = n_tile * BN + tid;
+        const size_t off = (size_t)(row / p.tab_div) * p.Cout + col;
+        tA[tid] = col < p.Cout ? __ldg(p.tabA + off) : 0.f;
+        tB[tid] = col < p.Cout ? __ldg(p.tabB + off) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
       constexpr int COLS = BN / (EPI_WARPS / 4);  // columns drained by this warp
@@ -185,13 +194,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
       const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
-#pragma unroll 2
-      for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
-        if (n_tile * BN + c0 >= p.Cout) break;  // zero-padded output channels of a ragged last n-tile (warp-uniform)
-        uint32_t v[8];
-        tmem_ld8(taddr + c0, v);
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(tA + c0)), a1 = __ldg(reinterpret_cast<const float4*>(tA + c0 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(tB + c0)), b1 = __ldg(reinterpret_cast<const float4*>(tB + c0 + 4));
+#pragma unroll 1
+      for (int cg = cbeg; cg < cbeg + COLS; cg += 32) {
+        if (n_tile * BN + cg >= p.Cout) break;  // zero-padded output channels of a ragged last n-tile (warp-uniform)
+        uint32_t v32[32];
+        tmem_ld32_nowait(taddr + cg, v32);
+        tmem_ld_wait();
+#pragma unroll
+      for (int cs = 0; cs < 32; cs += 8) {
+        const int c0 = cg + cs;
+        if (n_tile * BN + c0 >= p.Cout) break;
+        const uint32_t* v = v32 + cs;
+        const float4 a0 = *reinterpret_cast<const float4*>(tA + c0), a1 = *reinterpret_cast<const float4*>(tA + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(tB + c0), b1 = *reinterpret_cast<const float4*>(tB + c0 + 4);
         float y[8];
         y[0] = fmaf(__uint_as_float(v[0]), a0.x, b0.x); y[1] = fmaf(__uint_as_float(v[1]), a0.y, b0.y);
         y[2] = fmaf(__uint_as_float(v[2]), a0.z, b0.z); y[3] = fmaf(__uint_as_float(v[3]), a0.w, b0.w);
@@ -230,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
           }
           *reinterpret_cast<uint4*>(orow + c0) = pack8(y);
         }
+      }
       }
       }
       tc_fence_before();                                    // all tcgen05.ld of this accumulator have completed
@@ -340,9 +356,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
             for (int t = 0; t < GT; ++t) {
               const int tap = g * GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
               const int a_off = TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
+              constexpr int TILE_STEP = TILE_W * (TMA ? 128 : 16);  // 8 pixels further along the patch row
 #pragma unroll
               for (int tile = 0; tile < T; ++tile)
-                umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_W * 128) >> 4),
+                umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_STEP) >> 4),
                                          b_st + (uint64_t)((t * B_TAP) >> 4), idesc, tap ? 1u : (uint32_t)(c != 0), leader);
             }
             if (!b_resident) umma_commit_if(bar_b_empty + sb * 8, leader);  // weight stage free once these MMAs retire
@@ -411,15 +428,15 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 // A / B = patch / weight ring depths.
 template <int MODE, int BN, bool TMA> struct Stages;
 template <> struct Stages<S1K3, 64, true> { static constexpr int T = 2, GT = 1, A = 3, B = 9; };    // 123 KB patches +  72 KB weights
-template <> struct Stages<S1K3, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };   //  82 KB patches + 144 KB weights
+template <> struct Stages<S1K3, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   //  82 KB patches + 128 KB weights
 template <> struct Stages<S1K3, 64, false> { static constexpr int T = 1, GT = 3, A = 6, B = 3; };
 template <> struct Stages<S1K3, 128, false> { static constexpr int T = 1, GT = 3, A = 3, B = 3; };
 template <> struct Stages<S1K1, 64, true> { static constexpr int T = 2, GT = 1, A = 5, B = 4; };
 template <> struct Stages<S1K1, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };
 template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
-template <> struct Stages<S2K4, 64, false> { static constexpr int T = 1, GT = 4, A = 4, B = 3; };   // 157 KB patches +  48 KB weights
-template <> struct Stages<S2K4, 128, false> { static constexpr int T = 1, GT = 4, A = 3, B = 3; };  // 118 KB patches +  96 KB weights
+template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
+template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
 static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
@@ -438,11 +455,11 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
 
 template <int BN, int MODE, bool TMA>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  using G = Geo<MODE>;
   using St = Stages<MODE, BN, TMA>;
   constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
-  constexpr int a_stage = TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE>::A_STAGE;
-  constexpr int smem = AS * a_stage + BS * GT * BN * G::CH * 2 + (int)sizeof(Barriers<AS, BS>) + 64;
+  using G = Geo<MODE, TMA ? 1 : T>;
+  constexpr int a_stage = TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE, T>::A_STAGE;
+  constexpr int smem = AS * a_stage + BS * GT * BN * G::CH * 2 + (((int)sizeof(Barriers<AS, BS>) + 15) & ~15) + 4 * BN * 4 + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(2 * T * BN <= 512, "TMEM budget exceeded");
   static int num_sms = 0;

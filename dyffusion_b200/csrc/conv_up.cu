@@ -62,13 +62,13 @@ struct __align__(8) UBarriers {
 };
 
 // Fused epilogue of 8 consecutive GEMM columns (one parity class, channels co..co+7) of low-res pixel (i, j).
-__device__ __forceinline__ void up_store8(const UpConvParams& p, int img, int i, int j, int n, float* y) {
+// tA / tB point at the 8 table entries of these columns (global memory, or the per-item copy in shared memory).
+__device__ __forceinline__ void up_store8(const UpConvParams& p, int img, int i, int j, int n, float* y, const float* tA,
+                                          const float* tB) {
   const int cls = n / p.Cout, co = n - cls * p.Cout;
   const int oy = 2 * i + (cls >> 1), ox = 2 * j + (cls & 1);
-  const float* const tA = p.tabA + (size_t)(img / p.tab_div) * p.Cout + co;
-  const float* const tB = p.tabB + (size_t)(img / p.tab_div) * p.Cout + co;
-  const float4 a0 = __ldg(reinterpret_cast<const float4*>(tA)), a1 = __ldg(reinterpret_cast<const float4*>(tA) + 1);
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(tB)), b1 = __ldg(reinterpret_cast<const float4*>(tB) + 1);
+  const float4 a0 = *reinterpret_cast<const float4*>(tA), a1 = *(reinterpret_cast<const float4*>(tA) + 1);
+  const float4 b0 = *reinterpret_cast<const float4*>(tB), b1 = *(reinterpret_cast<const float4*>(tB) + 1);
   y[0] = fmaf(y[0], a0.x, b0.x); y[1] = fmaf(y[1], a0.y, b0.y); y[2] = fmaf(y[2], a0.z, b0.z); y[3] = fmaf(y[3], a0.w, b0.w);
   y[4] = fmaf(y[4], a1.x, b1.x); y[5] = fmaf(y[5], a1.y, b1.y); y[6] = fmaf(y[6], a1.z, b1.z); y[7] = fmaf(y[7], a1.w, b1.w);
 #pragma unroll
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
   uint8_t* sB = smem + AS * A_STAGE;
   using Bars = UBarriers<AS, BS>;
   Bars* bars = reinterpret_cast<Bars*>(sB + BS * B_TAP);
+  float* sTab = reinterpret_cast<float*>(sB + BS * B_TAP + ((sizeof(Bars) + 15) & ~15));  // [2 acc][A | B][BN] epilogue tables
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nch0 = p.C[0] >> 6, nchunks = (p.C[0] + p.C[1]) >> 6;
@@ -146,6 +147,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
       int n_tile, img, i0, j0, side;
       decode(w, n_tile, img, i0, j0, side);
       const int acc = it & 1;
+      float* const tA = sTab + acc * 2 * BN;  // this item's epilogue tables, staged once in shared memory
+      float* const tB = tA + BN;
+      if (tid < BN) {
+        const size_t off = (size_t)(img / p.tab_div) * p.Cout + (n_tile * BN + tid) % p.Cout;
+        tA[tid] = __ldg(p.tabA + off);
+        tB[tid] = __ldg(p.tabB + off);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -163,15 +172,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
           valid = i >= 1 && i <= p.H - 2;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
-#pragma unroll 2
-        for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 8) {
-          uint32_t v[8];
-          tmem_ld8(taddr + c0, v);
+#pragma unroll 1
+        for (int cg = cbeg; cg < cbeg + COLS; cg += 32) {
+          uint32_t v[32];
+          tmem_ld32_nowait(taddr + cg, v);
+          tmem_ld_wait();
           if (valid) {
-            float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[e]);
-            up_store8(p, img, i, j, n_tile * BN + c0, y);
+            for (int cs = 0; cs < 32; cs += 8) {
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[cs + e]);
+              up_store8(p, img, i, j, n_tile * BN + cg + cs, y, tA + cg + cs, tB + cg + cs);
+            }
           }
         }
       }
@@ -278,11 +291,15 @@ __global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams 
   const int bottom = corner >> 1, right = corner & 1;
   const int i = bottom ? p.H - 1 : 0, j = right ? p.W - 1 : 0;
   const int nimg = min(CORNER_IMGS, p.rows - img0);
-  for (int e = threadIdx.x; e < CORNER_IMGS * K; e += blockDim.x) {
-    const int c = e % Cin, t = (e / Cin) & 3, im = e / K;
+  for (int e8 = threadIdx.x; e8 < CORNER_IMGS * K / 8; e8 += blockDim.x) {  // 8 channels (one 128-bit load) per step
+    const int e = e8 * 8, c = e % Cin, t = (e / Cin) & 3, im = e / K;
     const int ii = i + (t >> 1) - bottom, jj = j + (t & 1) - right;  // taps (di, dj) in {0,1}^2 (top/left) or {-1,0}^2
     const int s = c < p.C[0] ? 0 : 1, cs = s ? c - p.C[0] : c;
-    sx[e] = im < nimg ? __bfloat162float(p.src[s][(((size_t)(img0 + im) * p.H + ii) * p.W + jj) * p.ld[s] + cs]) : 0.f;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (im < nimg)
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.src[s] + (((size_t)(img0 + im) * p.H + ii) * p.W + jj) * p.ld[s] + cs)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sx[e + k] = f[k];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -296,7 +313,7 @@ __global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams 
   if (n0 < N) {
     const float* wc = p.wc + (size_t)corner * K * N + n0;
     const int per = K / 8;
-#pragma unroll 4
+#pragma unroll 8
     for (int tc = slice * per; tc < (slice + 1) * per; ++tc) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N) + 1);
@@ -324,7 +341,8 @@ __global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams 
       for (int sl = 0; sl < 8; ++sl) v += red[((sl * CORNER_IMGS + im) * 32 + lane) * 8 + e];
       y[e] = v;
     }
-    up_store8(p, img0 + im, i, j, n0, y);
+    const size_t toff = (size_t)((img0 + im) / p.tab_div) * p.Cout + n0 % p.Cout;
+    up_store8(p, img0 + im, i, j, n0, y, p.tabA + toff, p.tabB + toff);
   }
 }
 
@@ -383,7 +401,7 @@ void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
 template <int KIND>
 int launch_kind(const UpConvParams& p, cudaStream_t stream) {
   using G = UGeo<KIND>;
-  constexpr int smem = G::AS * G::A_STAGE + G::BS * B_TAP + (int)sizeof(UBarriers<G::AS, G::BS>) + 64;
+  constexpr int smem = G::AS * G::A_STAGE + G::BS * B_TAP + (((int)sizeof(UBarriers<G::AS, G::BS>) + 15) & ~15) + 4 * BN * 4 + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static int num_sms = 0;
   if (!num_sms) {
