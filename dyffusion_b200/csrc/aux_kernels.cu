@@ -69,7 +69,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
 
 // ------------------------------------------------------------------------------------------------ pack, space-to-depth
 // One thread per (block pixel, sub-position): 16 channel slots = C_in resized input channels, a ones slot, zeros.
-__global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p) {
+// The concat is flattened on the host into per-channel plane pointers (S2dChannels), so the per-thread work is the four
+// bilinear taps per channel and two 128-bit stores.
+struct S2dChannels {
+  const float* plane[16];  // channel plane of source row 0
+  int row_stride[16];      // floats between consecutive source rows of that tensor
+  int n;                   // real channels (slot n carries 1.0)
+};
+__global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const S2dChannels ch) {
   const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -87,28 +94,18 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p) {
     bilinear_coord(ox, p.Wi, (float)p.Wi / (float)Wf, x0, x1, lx);
   }
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const size_t plane = (size_t)p.Hi * p.Wi;
-  // flattened concat channel -> plane pointer (uniform, computed once per thread; nsrc <= 6, at most 15 channels)
   const int o00 = y0 * p.Wi + x0, o01 = y0 * p.Wi + x1, o10 = y1 * p.Wi + x0, o11 = y1 * p.Wi + x1;
-  int cbeg[7];
-  cbeg[0] = 0;
-#pragma unroll
-  for (int s = 0; s < 6; ++s) cbeg[s + 1] = cbeg[s] + (s < p.nsrc ? p.C[s] : 0);
+  const int rs = r % p.src_rows;
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {  // compile-time slot index: all gathers are issued before any is consumed
-    float val = 0.f;
-    if (i < cbeg[6]) {
-      const float* sb = p.src[0];
-      int sc = p.C[0], s0 = 0;
-#pragma unroll
-      for (int k = 1; k < 6; ++k)
-        if (k < p.nsrc && i >= cbeg[k]) { sb = p.src[k]; sc = p.C[k]; s0 = cbeg[k]; }
-      const float* pl = sb + ((size_t)(r % p.src_rows) * sc + (i - s0)) * plane;
+    float val = i == ch.n ? 1.f : 0.f;
+    if (i < ch.n) {
+      const float* pl = ch.plane[i] + (size_t)rs * ch.row_stride[i];
       val = p.bilinear ? w00 * __ldg(pl + o00) + w01 * __ldg(pl + o01) + w10 * __ldg(pl + o10) + w11 * __ldg(pl + o11)
-                       : __ldg(pl + (size_t)oy * p.Wi + ox);
+                       : __ldg(pl + o00);
     }
-    v[i] = i == p.ones_channel ? 1.f : val;
+    v[i] = val;
   }
   uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)blk * 64 + sub * 16);
   o[0] = pack8(v);
@@ -685,8 +682,15 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
     for (int i = 0; i < p.nsrc; ++i) ctot += p.C[i];
     if (ctot > 15 || p.ones_channel != ctot || p.noise_src >= 0) { set_error("pack s2d: needs <= 15 input channels"); return -1; }
     const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
+    S2dChannels ch{};
+    const size_t plane = (size_t)p.Hi * p.Wi;
+    for (int i = 0; i < p.nsrc; ++i)
+      for (int c = 0; c < p.C[i]; ++c, ++ch.n) {
+        ch.plane[ch.n] = p.src[i] + (size_t)c * plane;
+        ch.row_stride[ch.n] = (int)(p.C[i] * plane);
+      }
     ProfScope prof(s, KC_PACK);
-    pack_s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+    pack_s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(p, ch);
     DYF_LAUNCH_OK("pack_s2d_kernel");
     return 0;
   }

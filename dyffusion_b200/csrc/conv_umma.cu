@@ -426,9 +426,14 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 
 // Pipeline shapes that fill the 227 KB of one SM.  T = pixel tiles per work item (TMA mode), GT = taps per weight stage,
 // A / B = patch / weight ring depths.
-template <int MODE, int BN, bool TMA> struct Stages;
+// V = shape variant: 0 = default; 1 = single-chunk layers (Cin == one chunk, one n-tile, e.g. the NS stem): the whole
+// filter stays resident in the weight ring and the freed L2 bandwidth + a deeper patch ring feed the short tiles;
+// 2, 3 = experiment shapes of the stride-2 kernel (DYF_S2K4_CFG).
+template <int MODE, int BN, bool TMA, int V = 0> struct Stages;
 template <> struct Stages<S1K3, 64, true> { static constexpr int T = 2, GT = 1, A = 3, B = 9; };    // 123 KB patches +  72 KB weights
 template <> struct Stages<S1K3, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   //  82 KB patches + 128 KB weights
+template <> struct Stages<S1K3, 64, true, 1> { static constexpr int T = 2, GT = 1, A = 3, B = 9; };
+template <> struct Stages<S1K3, 128, true, 1> { static constexpr int T = 1, GT = 1, A = 3, B = 9; };  //  69 KB patches + 144 KB resident filter
 template <> struct Stages<S1K3, 64, false> { static constexpr int T = 1, GT = 3, A = 6, B = 3; };
 template <> struct Stages<S1K3, 128, false> { static constexpr int T = 1, GT = 3, A = 3, B = 3; };
 template <> struct Stages<S1K1, 64, true> { static constexpr int T = 2, GT = 1, A = 5, B = 4; };
@@ -437,6 +442,8 @@ template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1,
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
+template <> struct Stages<S2K4, 128, false, 2> { static constexpr int T = 1, GT = 1, A = 2, B = 17; };  //  77 KB patches + 136 KB weights
+template <> struct Stages<S2K4, 128, false, 3> { static constexpr int T = 1, GT = 1, A = 4, B = 8; };   // 154 KB patches +  64 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
 static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
@@ -453,9 +460,9 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
   return 0;
 }
 
-template <int BN, int MODE, bool TMA>
+template <int BN, int MODE, bool TMA, int V = 0>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  using St = Stages<MODE, BN, TMA>;
+  using St = Stages<MODE, BN, TMA, V>;
   constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
   using G = Geo<MODE, TMA ? 1 : T>;
   constexpr int a_stage = TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE, T>::A_STAGE;
@@ -520,7 +527,9 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   //  and UMMA reads alike -- verified on hardware)
   if (mode == S1K3) {
     if (want_tma) {
-      const int rc = n64 ? launch_t<64, S1K3, true>(p, stream) : launch_t<128, S1K3, true>(p, stream);
+      const bool single = p.Cin == 64 && p.Cout <= 128;  // one chunk, one n-tile: resident filter
+      const int rc = n64 ? launch_t<64, S1K3, true>(p, stream)
+                         : single ? launch_t<128, S1K3, true, 1>(p, stream) : launch_t<128, S1K3, true>(p, stream);
       if (rc != 0) return rc;
     }
     return n64 ? launch_t<64, S1K3, false>(p, stream) : launch_t<128, S1K3, false>(p, stream);
@@ -532,6 +541,9 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     }
     return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
   }
+  static const char* env_c = getenv("DYF_S2K4_CFG");
+  if (!n64 && env_c && env_c[0] == '2') return launch_t<128, S2K4, false, 2>(p, stream);
+  if (!n64 && env_c && env_c[0] == '3') return launch_t<128, S2K4, false, 3>(p, stream);
   return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
 }
 

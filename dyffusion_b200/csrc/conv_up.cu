@@ -55,11 +55,21 @@ template <> struct UGeo<K_COL> {   // 128 consecutive pixels of the first / last
   __device__ static constexpr int tap_off(int ty, int tx) { return tx * REGION + ty * 128; }
 };
 
-template <int AS, int BS>
-struct __align__(8) UBarriers {
-  uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
+// One launch runs the three tile kinds back to back as phases of the same persistent CTAs (a CTA that runs out of
+// MAIN tiles moves on to ROW / COL tiles without waiting for the others).  The barrier block and the epilogue tables sit
+// at a fixed offset behind the largest A/B ring; barriers are re-initialised between phases.
+constexpr int MAX_AS = 2, MAX_BS = 8;
+struct __align__(16) UBarriers {
+  uint64_t a_full[MAX_AS], a_empty[MAX_AS], b_full[MAX_BS], b_empty[MAX_BS], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+template <int KIND> constexpr int ring_bytes() { return UGeo<KIND>::AS * UGeo<KIND>::A_STAGE + UGeo<KIND>::BS * B_TAP; }
+constexpr int BAR_OFF = cmax(ring_bytes<K_MAIN>(), cmax(ring_bytes<K_ROW>(), ring_bytes<K_COL>()));
+constexpr int TAB_OFF = BAR_OFF + (((int)sizeof(UBarriers) + 15) & ~15);
+constexpr int SMEM_BYTES = TAB_OFF + 4 * BN * 4 + 64;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+struct UpWork { int tiles_a[3], num_work[3]; };  // per kind: tile blocks along the tiled axis, work items
 
 // Fused epilogue of 8 consecutive GEMM columns (one parity class, channels co..co+7) of low-res pixel (i, j).
 // tA / tB point at the 8 table entries of these columns (global memory, or the per-item copy in shared memory).
@@ -83,35 +93,18 @@ __device__ __forceinline__ void up_store8(const UpConvParams& p, int img, int i,
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams p, int tiles_a, int n_tiles, int num_work,
-                                                             const __grid_constant__ CUtensorMap tmap0,
-                                                             const __grid_constant__ CUtensorMap tmap1) {
+__device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, uint32_t tmem_base, int tiles_a, int n_tiles,
+                                         int num_work, const CUtensorMap* tmap0, const CUtensorMap* tmap1) {
   using G = UGeo<KIND>;
   constexpr int AS = G::AS, BS = G::BS, T = G::T, A_STAGE = G::A_STAGE;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  static_assert(AS <= MAX_AS && BS <= MAX_BS, "barrier block too small");
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS * A_STAGE;
-  using Bars = UBarriers<AS, BS>;
-  Bars* bars = reinterpret_cast<Bars*>(sB + BS * B_TAP);
-  float* sTab = reinterpret_cast<float*>(sB + BS * B_TAP + ((sizeof(Bars) + 15) & ~15));  // [2 acc][A | B][BN] epilogue tables
+  UBarriers* bars = reinterpret_cast<UBarriers*>(smem + BAR_OFF);
+  float* sTab = reinterpret_cast<float*>(smem + TAB_OFF);  // [2 acc][A | B][BN] epilogue tables
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nch0 = p.C[0] >> 6, nchunks = (p.C[0] + p.C[1]) >> 6;
-
-  if (tid == 0) {
-    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
-    for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == EPI_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * T * BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
 
   // work item -> (n_tile, image, side | tile origin).  MAIN: tiles_a = tiles_x (16-pixel blocks per row); ROW / COL:
   // tiles_a = 128-pixel blocks along the border, `side` 0 = first row / column, 1 = last.
@@ -203,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
           mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
           const uint32_t bar = smem_u32(&bars->a_full[st]);
           mbar_expect_tx(bar, G::NBOX * G::BW * G::BH * 128);
-          const uint64_t tm = reinterpret_cast<uint64_t>(c < nch0 ? &tmap0 : &tmap1);
+          const uint64_t tm = reinterpret_cast<uint64_t>(c < nch0 ? tmap0 : tmap1);
           const int cc = (c < nch0 ? c : c - nch0) * 64;
 #pragma unroll
           for (int b = 0; b < G::NBOX; ++b) {
@@ -273,10 +266,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams p, const UpWork wk, int n_tiles,
+                                                             const __grid_constant__ CUtensorMap tm_main0,
+                                                             const __grid_constant__ CUtensorMap tm_main1,
+                                                             const __grid_constant__ CUtensorMap tm_row0,
+                                                             const __grid_constant__ CUtensorMap tm_row1,
+                                                             const __grid_constant__ CUtensorMap tm_col0,
+                                                             const __grid_constant__ CUtensorMap tm_col1) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  UBarriers* bars = reinterpret_cast<UBarriers*>(smem + BAR_OFF);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == EPI_WARPS + 1) {  // TMEM: two accumulator sets of (up to) two 128-column tiles, owned by the MMA warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+#pragma unroll 1
+  for (int phase = 0; phase < 3; ++phase) {
+    if (tid == 0) {
+      for (int i = 0; i < MAX_AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+      for (int i = 0; i < MAX_BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    if (phase == 0) up_phase<K_MAIN>(p, smem, tmem_base, wk.tiles_a[0], n_tiles, wk.num_work[0], &tm_main0, &tm_main1);
+    else if (phase == 1) up_phase<K_ROW>(p, smem, tmem_base, wk.tiles_a[1], n_tiles, wk.num_work[1], &tm_row0, &tm_row1);
+    else up_phase<K_COL>(p, smem, tmem_base, wk.tiles_a[2], n_tiles, wk.num_work[2], &tm_col0, &tm_col1);
+    tc_fence_before();
+    __syncthreads();  // every role of this CTA has drained the phase: barriers can be re-initialised
+  }
   if (warp == EPI_WARPS + 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * T * BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(bars->tmem_base), "r"(512));
   }
 }
 
@@ -398,48 +423,50 @@ void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
       }
 }
 
-template <int KIND>
-int launch_kind(const UpConvParams& p, cudaStream_t stream) {
-  using G = UGeo<KIND>;
-  constexpr int smem = G::AS * G::A_STAGE + G::BS * B_TAP + (((int)sizeof(UBarriers<G::AS, G::BS>) + 15) & ~15) + 4 * BN * 4 + 64;
-  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+int launch_phases(const UpConvParams& p, cudaStream_t stream) {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     DYF_CUDA_OK(cudaGetDevice(&dev));
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
-  CUtensorMap tm[2];
-  for (int s = 0; s < 2; ++s) {
-    const int sidx = p.C[s] ? s : 0;  // single-source layers: the second map is never used
-    const Key key{p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], KIND};
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-      CUtensorMap m;
-      if (make_nhwc_tmap(p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], G::BW, G::BH, 1, &m) != 0) {
-        set_error("conv_up: cuTensorMapEncodeTiled failed");
-        return -1;
+  const int bw[3] = {UGeo<K_MAIN>::BW, UGeo<K_ROW>::BW, UGeo<K_COL>::BW};
+  const int bh[3] = {UGeo<K_MAIN>::BH, UGeo<K_ROW>::BH, UGeo<K_COL>::BH};
+  CUtensorMap tm[3][2];
+  for (int k = 0; k < 3; ++k)
+    for (int s = 0; s < 2; ++s) {
+      const int sidx = p.C[s] ? s : 0;  // single-source layers: the second map is never used
+      const Key key{p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], k};
+      auto it = cache.find(key);
+      if (it == cache.end()) {
+        CUtensorMap m;
+        if (make_nhwc_tmap(p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], bw[k], bh[k], 1, &m) != 0) {
+          set_error("conv_up: cuTensorMapEncodeTiled failed");
+          return -1;
+        }
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(key, m).first;
       }
-      if (cache.size() > 4096) cache.clear();
-      it = cache.emplace(key, m).first;
+      tm[k][s] = it->second;
     }
-    tm[s] = it->second;
-  }
   const int n_tiles = 4 * p.Cout / BN;
-  const int tiles_a = KIND == K_MAIN ? (p.W + 15) / 16 : KIND == K_ROW ? (p.W + 127) / 128 : (p.H + 127) / 128;
-  const long long work = KIND == K_MAIN ? (long long)tiles_a * ((p.H + 15) / 16) * p.rows * n_tiles
-                                        : (long long)2 * tiles_a * p.rows * n_tiles;
-  if (work > 0x7fffffffLL) { set_error("conv_up: too many tiles"); return -1; }
-  const int grid = (int)(work < num_sms ? work : num_sms);
+  UpWork wk;
+  wk.tiles_a[0] = (p.W + 15) / 16; wk.tiles_a[1] = (p.W + 127) / 128; wk.tiles_a[2] = (p.H + 127) / 128;
+  const long long work[3] = {(long long)wk.tiles_a[0] * ((p.H + 15) / 16) * p.rows * n_tiles,
+                             (long long)2 * wk.tiles_a[1] * p.rows * n_tiles, (long long)2 * wk.tiles_a[2] * p.rows * n_tiles};
+  for (int k = 0; k < 3; ++k) {
+    if (work[k] > 0x7fffffffLL) { set_error("conv_up: too many tiles"); return -1; }
+    wk.num_work[k] = (int)work[k];
+  }
+  const int grid = (int)(work[0] < num_sms ? work[0] : num_sms);
   const int Cin = p.C[0] + p.C[1];
-  // algorithmic FLOPs of the reference's conv are booked on the MAIN launch (border launches recompute ring pixels)
-  const double flops = KIND == K_MAIN ? 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin : 0.0;
-  const double bytes = KIND == K_MAIN ? 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin) : 0.0;
+  const double flops = 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin;  // = the reference conv on the upsampled grid
+  const double bytes = 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_up_kernel<KIND><<<grid, THREADS, smem, stream>>>(p, tiles_a, n_tiles, (int)work, tm[0], tm[1]);
+  conv_up_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p, wk, n_tiles, tm[0][0], tm[0][1], tm[1][0], tm[1][1], tm[2][0], tm[2][1]);
   DYF_LAUNCH_OK("conv_up_kernel");
   return 0;
 }
@@ -489,9 +516,7 @@ int launch_conv_up(const UpConvParams& p, cudaStream_t stream) {
     set_error("conv_up: unsupported shape");
     return -1;
   }
-  int rc = launch_kind<K_MAIN>(p, stream);
-  if (!rc) rc = launch_kind<K_ROW>(p, stream);
-  if (!rc) rc = launch_kind<K_COL>(p, stream);
+  int rc = launch_phases(p, stream);
   if (rc) return rc;
   const int Cin = p.C[0] + p.C[1];
   const size_t smem = ((size_t)CORNER_IMGS * 4 * Cin + 8 * CORNER_IMGS * 32 * 8) * sizeof(float);

@@ -1,0 +1,103 @@
+"""GPU tests of the fused decoder block (conv_up.cu): bilinear x2 upsample + skip concat + 3x3 conv as ONE composite
+tcgen05 conv on the low-resolution grid (reference: src/models/unet_simple.py:41-51, :133-140).
+
+The two-kernel path (upsample kernel + conv kernel, `DYF_DISABLE_UPFUSE=1` at net creation) is the in-engine reference;
+the oracle is the external one.  The composite rounds *composite weights* to bf16 where the two-kernel path rounds the
+upsampled activations, so the two agree to bf16 noise, not bit for bit: tolerance rel-L2 <= 1e-2 per forward (the NS
+tolerance of tests/test_gpu_parity.py).  Border handling is exact algebra (own weight variants for the first / last
+row / column and the corners); a wrong border would show up as an O(1) error on the outer ring, so the ring is checked
+separately at the same tolerance."""
+import os
+
+import pytest
+import torch
+
+from oracle import dyffusion_oracle as O
+from oracle.synth import synth_state_dict, synth_tensor
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _build(up, fuse, fuse_min=None, dropout=0.0, seed=6):
+    from dyffusion_b200.backbones import UNet
+    saved = {k: os.environ.pop(k, None) for k in ("DYF_DISABLE_UPFUSE", "DYF_UPFUSE_MIN")}
+    try:
+        if not fuse:
+            os.environ["DYF_DISABLE_UPFUSE"] = "1"
+        if fuse_min:
+            os.environ["DYF_UPFUSE_MIN"] = str(fuse_min)
+        m = UNet(dim=64, with_time_emb=True, upsample_dims=up, dropout=dropout, num_input_channels=3,
+                 num_output_channels=3, num_conditional_channels=2, spatial_shape=(221, 42), verbose=False)
+    finally:
+        for k in ("DYF_DISABLE_UPFUSE", "DYF_UPFUSE_MIN"):
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=seed)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), sd
+
+
+def _inputs(rows):
+    x = synth_tensor("uf.x", (rows, 3, 221, 42)).cuda()
+    c = synth_tensor("uf.c", (rows, 2, 221, 42), kind="mask").cuda()
+    t = torch.linspace(0.0, 7.0, rows).cuda()
+    return x, c, t
+
+
+def _ring(y, w=4):
+    m = torch.zeros_like(y, dtype=torch.bool)
+    m[..., :w, :] = True; m[..., -w:, :] = True; m[..., :, :w] = True; m[..., :, -w:] = True
+    return m
+
+
+# (network grid, smallest fused upsampled side): 256^2 is the shipped NS grid (two fused blocks); the others force the
+# fused kernel onto small / non-square grids (row tiles narrower than 128 pixels, one main tile per image, ...).
+@pytest.mark.parametrize("up,fuse_min", [((256, 256), None), ((256, 256), 32), ((128, 192), 32), ((64, 64), 32), ((64, 128), 32)])
+def test_fused_block_matches_two_kernel_path_and_oracle(up, fuse_min):
+    rows = 3
+    x, c, t = _inputs(rows)
+    with torch.no_grad():
+        mf, sd = _build(up, True, fuse_min)
+        yf = mf(x, time=t, condition=c).cpu()
+        mu, _ = _build(up, False)
+        yu = mu(x, time=t, condition=c).cpu()
+        yo = O.unet_simple_forward(sd, x.cpu(), t.cpu(), c.cpu(), dim=64, upsample_dims=up)
+    assert torch.isfinite(yf).all()
+    assert H.rel_l2(yf, yu) <= TOL, H.rel_l2(yf, yu)
+    assert H.rel_l2(yf, yo) <= TOL, H.rel_l2(yf, yo)
+    ring = _ring(yf)
+    e_ring = float((yf[ring] - yo[ring]).norm() / yo[ring].norm())
+    e_int = float((yf[~ring] - yo[~ring]).norm() / yo[~ring].norm())
+    assert e_ring <= TOL and e_int <= TOL, (e_ring, e_int)
+
+
+def test_fused_block_rows_are_independent_and_reproducible():
+    x, c, t = _inputs(5)
+    with torch.no_grad():
+        m, _ = _build((256, 256), True)
+        y = m(x, time=t, condition=c)
+        y2 = m(x, time=t, condition=c)
+        y1 = m(x[3:4], time=t[3:4], condition=c[3:4])
+    assert torch.equal(y, y2)
+    assert torch.equal(y[3:4], y1)
+
+
+def test_fused_block_draws_the_same_dropout_masks():
+    """Dropout masks are a pure function of (seed, call, site, hi-res element index): the depth-to-space epilogue must
+    draw the same masks as the two-kernel path, so with dropout ON the two paths still agree to bf16 noise."""
+    x, c, t = _inputs(2)
+    outs = []
+    with torch.no_grad():
+        for fuse in (True, False):
+            m, _ = _build((256, 256), fuse, dropout=0.15)
+            torch.manual_seed(77)
+            m._drop_stream = 0
+            with m.inference_dropout_scope(True):
+                outs.append(m(x, time=t, condition=c).cpu())
+        m0, _ = _build((256, 256), True, dropout=0.15)
+        y_nodrop = m0(x, time=t, condition=c).cpu()
+    assert H.rel_l2(outs[0], outs[1]) <= 2 * TOL, H.rel_l2(outs[0], outs[1])
+    assert H.rel_l2(outs[0], y_nodrop) > 5 * TOL  # dropout was really on
