@@ -33,7 +33,9 @@ namespace {
 
 constexpr int TILE_H = 16, TILE_W = 8;  // output pixels per CTA tile (M = 128)
 constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each draining half of the accumulator columns
-constexpr int THREADS = (EPI_WARPS + 4 + 2) * 32;  // epilogue + 4 producer warps + MMA warp + weight-stream warp
+// epilogue + patch-producer warps (1 issuing thread with TMA, 8 gathering warps with cp.async) + MMA warp + weight warp
+__host__ __device__ constexpr int prod_warps(bool tma) { return tma ? 1 : 8; }
+__host__ __device__ constexpr int cta_threads(bool tma) { return (EPI_WARPS + prod_warps(tma) + 2) * 32; }
 
 enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2 };
 
@@ -107,11 +109,12 @@ struct __align__(8) Barriers {
 // is released, so a weight byte pulled from L2 feeds T x 128 GEMM rows; the patch of the 16 x 8T super-tile is one TMA
 // box and each tile's taps are start-address shifts inside it.  GT = filter taps per weight stage.
 template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
-__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
+__global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
+  constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
   constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
   static_assert(TMA || T == 1 || MODE == S2K4, "multi-tile gathered patches: stride-2 mode only");
   static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
@@ -134,12 +137,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   const bool b_resident = n_tiles == 1 && nchunks * (G::TAPS / GT) == BS;
 
   if (tid == 0) {
-    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TMA ? 1 : 128); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
+    for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TMA ? 1 : PROD_THREADS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
     for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == EPI_WARPS + 4) {  // TMEM: two accumulators of BN fp32 columns, owned by the MMA warp
+  if (warp == MMA_WARP) {  // TMEM: two accumulators of BN fp32 columns, owned by the MMA warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(2 * T * BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   if (warp < EPI_WARPS) {
     // =============================== epilogue warps: TMEM -> registers -> fused math -> global ====================
     const int act = p.act;
+    const float slope = act == ACT_NONE ? 1.f : act == ACT_RELU ? 0.f : 0.2f;
     const uint32_t thresh = p.drop.thresh;
     const float dscale = p.drop.scale;
     int it = 0;
@@ -197,61 +201,59 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
 #pragma unroll 1
       for (int cg = cbeg; cg < cbeg + COLS; cg += 32) {
         if (n_tile * BN + cg >= p.Cout) break;  // zero-padded output channels of a ragged last n-tile (warp-uniform)
-        uint32_t v32[32];
-        tmem_ld32_nowait(taddr + cg, v32);
+        uint32_t v[32];
+        tmem_ld32_nowait(taddr + cg, v);
         tmem_ld_wait();
+        // 32 columns as one straight-line block (no per-8-column control flow: the scheduler interleaves the chains)
+        float y[32];
 #pragma unroll
-      for (int cs = 0; cs < 32; cs += 8) {
-        const int c0 = cg + cs;
-        if (n_tile * BN + c0 >= p.Cout) break;
-        const uint32_t* v = v32 + cs;
-        const float4 a0 = *reinterpret_cast<const float4*>(tA + c0), a1 = *reinterpret_cast<const float4*>(tA + c0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(tB + c0), b1 = *reinterpret_cast<const float4*>(tB + c0 + 4);
-        float y[8];
-        y[0] = fmaf(__uint_as_float(v[0]), a0.x, b0.x); y[1] = fmaf(__uint_as_float(v[1]), a0.y, b0.y);
-        y[2] = fmaf(__uint_as_float(v[2]), a0.z, b0.z); y[3] = fmaf(__uint_as_float(v[3]), a0.w, b0.w);
-        y[4] = fmaf(__uint_as_float(v[4]), a1.x, b1.x); y[5] = fmaf(__uint_as_float(v[5]), a1.y, b1.y);
-        y[6] = fmaf(__uint_as_float(v[6]), a1.z, b1.z); y[7] = fmaf(__uint_as_float(v[7]), a1.w, b1.w);
-        switch (act) {
-          case ACT_RELU:
+        for (int q = 0; q < 8; ++q) {
+          const float4 a = *reinterpret_cast<const float4*>(tA + cg + 4 * q), b = *reinterpret_cast<const float4*>(tB + cg + 4 * q);
+          y[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), a.x, b.x);
+          y[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), a.y, b.y);
+          y[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a.z, b.z);
+          y[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a.w, b.w);
+        }
+        if (act <= ACT_LEAKY) {  // identity / ReLU / LeakyReLU(0.2) = max(y, slope * y) with slope 1 / 0 / 0.2
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
-            break;
-          case ACT_LEAKY:
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], slope * y[j]);
+        } else if (act == ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = y[j] > 0.f ? y[j] : 0.2f * y[j];
-            break;
-          case ACT_SILU:
+          for (int j = 0; j < 32; ++j) y[j] = y[j] / (1.f + __expf(-y[j]));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = y[j] / (1.f + __expf(-y[j]));
-            break;
-          case ACT_GELU:
-#pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = 0.5f * y[j] * (1.f + erff(y[j] * 0.70710678118654752f));
-            break;
-          default: break;
+          for (int j = 0; j < 32; ++j) y[j] = 0.5f * y[j] * (1.f + erff(y[j] * 0.70710678118654752f));
         }
         if (thresh) {
-          const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + n_tile * BN + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = ((keep >> j) & 1u) ? y[j] * dscale : 0.f;
+          for (int cs = 0; cs < 32; cs += 8) {
+            const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + n_tile * BN + cg + cs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[cs + j] = ((keep >> j) & 1u) ? y[cs + j] * dscale : 0.f;
+          }
         }
         if (valid) {
           if (rrow) {
-            float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + c0)), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] += f[j];
+            for (int cs = 0; cs < 32; cs += 8) {
+              if (n_tile * BN + cg + cs < p.Cout) {
+                float f[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + cg + cs)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[cs + j] += f[j];
+              }
+            }
           }
-          *reinterpret_cast<uint4*>(orow + c0) = pack8(y);
+#pragma unroll
+          for (int cs = 0; cs < 32; cs += 8)
+            if (n_tile * BN + cg + cs < p.Cout) *reinterpret_cast<uint4*>(orow + cg + cs) = pack8(y + cs);
         }
-      }
       }
       }
       tc_fence_before();                                    // all tcgen05.ld of this accumulator have completed
       mbar_arrive(smem_u32(&bars->acc_empty[acc]));         // hand the accumulator back to the MMA warp
     }
-  } else if (warp < EPI_WARPS + 4) {
+  } else if (warp < MMA_WARP) {
     // =============================== A producers: halo patches via cp.async (zero fill = padding) ================
     const int ptid = tid - EPI_WARPS * 32;
     if constexpr (TMA) {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
         }
       }
     } else {
-    constexpr int PSTEP = 128 / G::CPL;                     // patch pixels covered per pass of the 128 threads
+    constexpr int PSTEP = PROD_THREADS / G::CPL;            // patch pixels covered per pass of the producer threads
     constexpr int ITERS = (G::PIX + PSTEP - 1) / PSTEP;
     const int g8 = ptid % G::CPL;                           // fixed 8-channel group of this thread
     const __nv_bfloat16* const in_base = p.in;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
       }
     }
     }
-  } else if (warp == EPI_WARPS + 4) {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA issuer (one elected thread) ==============================================
     // The issue loop is latency-critical (one thread feeds the whole tensor pipe): descriptors are advanced by adding
     // compile-time constants to pre-built low words, taps are fully unrolled, and barriers are touched once per
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const ConvParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS + 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * T * BN));
   }
 }
@@ -486,7 +488,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, THREADS, smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
+  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
                                                                                 (int)work, tmap);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;

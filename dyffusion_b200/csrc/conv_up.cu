@@ -71,25 +71,45 @@ constexpr int SMEM_BYTES = TAB_OFF + 4 * BN * 4 + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 struct UpWork { int tiles_a[3], num_work[3]; };  // per kind: tile blocks along the tiled axis, work items
 
-// Fused epilogue of 8 consecutive GEMM columns (one parity class, channels co..co+7) of low-res pixel (i, j).
-// tA / tB point at the 8 table entries of these columns (global memory, or the per-item copy in shared memory).
-__device__ __forceinline__ void up_store8(const UpConvParams& p, int img, int i, int j, int n, float* y, const float* tA,
-                                          const float* tB) {
-  const int cls = n / p.Cout, co = n - cls * p.Cout;
-  const int oy = 2 * i + (cls >> 1), ox = 2 * j + (cls & 1);
-  const float4 a0 = *reinterpret_cast<const float4*>(tA), a1 = *(reinterpret_cast<const float4*>(tA) + 1);
-  const float4 b0 = *reinterpret_cast<const float4*>(tB), b1 = *(reinterpret_cast<const float4*>(tB) + 1);
-  y[0] = fmaf(y[0], a0.x, b0.x); y[1] = fmaf(y[1], a0.y, b0.y); y[2] = fmaf(y[2], a0.z, b0.z); y[3] = fmaf(y[3], a0.w, b0.w);
-  y[4] = fmaf(y[4], a1.x, b1.x); y[5] = fmaf(y[5], a1.y, b1.y); y[6] = fmaf(y[6], a1.z, b1.z); y[7] = fmaf(y[7], a1.w, b1.w);
+// Fused epilogue of NG groups of 8 consecutive GEMM columns starting at column n (each group = one parity class, channels
+// co..co+7) of low-res pixel (i, j).  tA / tB point at the table entries of column n (global memory, or the per-item copy
+// in shared memory).  Straight-line code: the NG chains interleave.
+template <int NG>
+__device__ __forceinline__ void up_store(const UpConvParams& p, int img, int i, int j, int n, float* y, const float* tA,
+                                         const float* tB) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) y[e] = apply_act(y[e], p.act);
-  const long long m = ((long long)img * (2 * p.H) + oy) * (2 * p.W) + ox;  // hi-res pixel index (dropout element order)
-  if (p.drop.thresh) {
-    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + co);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = ((keep >> e) & 1u) ? y[e] * p.drop.scale : 0.f;
+  for (int q = 0; q < 2 * NG; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(tA + 4 * q), b = *reinterpret_cast<const float4*>(tB + 4 * q);
+    y[4 * q + 0] = fmaf(y[4 * q + 0], a.x, b.x); y[4 * q + 1] = fmaf(y[4 * q + 1], a.y, b.y);
+    y[4 * q + 2] = fmaf(y[4 * q + 2], a.z, b.z); y[4 * q + 3] = fmaf(y[4 * q + 3], a.w, b.w);
   }
-  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.out_ld + co) = pack8(y);
+  if (p.act <= ACT_LEAKY) {  // identity / ReLU / LeakyReLU(0.2) = max(y, slope * y)
+    const float slope = p.act == ACT_NONE ? 1.f : p.act == ACT_RELU ? 0.f : 0.2f;
+#pragma unroll
+    for (int e = 0; e < 8 * NG; ++e) y[e] = fmaxf(y[e], slope * y[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8 * NG; ++e) y[e] = apply_act(y[e], p.act);
+  }
+  long long m[NG];
+  int co[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const int ng = n + 8 * g, cls = ng / p.Cout;
+    co[g] = ng - cls * p.Cout;
+    // hi-res pixel index (also the dropout element order of the two-kernel path)
+    m[g] = ((long long)img * (2 * p.H) + 2 * i + (cls >> 1)) * (2 * p.W) + 2 * j + (cls & 1);
+  }
+  if (p.drop.thresh) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m[g] * p.Cout + co[g]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[8 * g + e] = ((keep >> e) & 1u) ? y[8 * g + e] * p.drop.scale : 0.f;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) *reinterpret_cast<uint4*>(p.out + (size_t)m[g] * p.out_ld + co[g]) = pack8(y + 8 * g);
 }
 
 template <int KIND>
@@ -171,13 +191,10 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
           tmem_ld32_nowait(taddr + cg, v);
           tmem_ld_wait();
           if (valid) {
+            float y[32];
 #pragma unroll
-            for (int cs = 0; cs < 32; cs += 8) {
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[cs + e]);
-              up_store8(p, img, i, j, n_tile * BN + cg + cs, y, tA + cg + cs, tB + cg + cs);
-            }
+            for (int e = 0; e < 32; ++e) y[e] = __uint_as_float(v[e]);
+            up_store<4>(p, img, i, j, n_tile * BN + cg, y, tA + cg, tB + cg);
           }
         }
       }
@@ -367,7 +384,7 @@ __global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams 
       y[e] = v;
     }
     const size_t toff = (size_t)((img0 + im) / p.tab_div) * p.Cout + n0 % p.Cout;
-    up_store8(p, img0 + im, i, j, n0, y, p.tabA + toff, p.tabB + toff);
+    up_store<1>(p, img0 + im, i, j, n0, y, p.tabA + toff, p.tabB + toff);
   }
 }
 
