@@ -89,6 +89,8 @@ struct ReadoutGatherParams {
 int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s);
 // ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] -> 1x1-conv weight [16 * Cout, Cin] (row (ky*4+kx)*Cout + co)
 int launch_convt_to_conv1x1(const float* wt, float* out, int Cin, int Cout, cudaStream_t s);  // -> fp32 [16*Cout, Cin]
+// Conv2d(k2, s2, p0) weight fp32 [O, C, 2, 2] -> 1x1-conv weight [O, 4C] over the space-to-depth view of the input
+int launch_k2s2_to_conv1x1(const float* w, float* out, int O, int C, cudaStream_t s);
 
 // ---- attention blocks of the SST backbone (attn_kernels.cu)
 struct ChannelLNParams {

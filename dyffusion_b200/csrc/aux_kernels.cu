@@ -770,6 +770,20 @@ int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s) {
   return 0;
 }
 
+// Conv2d weight [O, C, 2, 2] -> 1x1-conv weight [O, 4C] over the space-to-depth view, K index = (ky*2 + kx)*C + ci
+__global__ void k2s2_to_conv1x1_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
+  const int o = blockIdx.x;
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    const int t = i / C, ci = i - t * C;
+    out[(size_t)o * 4 * C + i] = w[((size_t)o * C + ci) * 4 + t];
+  }
+}
+int launch_k2s2_to_conv1x1(const float* w, float* out, int O, int C, cudaStream_t s) {
+  k2s2_to_conv1x1_kernel<<<O, 256, 0, s>>>(w, out, C);
+  DYF_LAUNCH_OK("k2s2_to_conv1x1_kernel");
+  return 0;
+}
+
 int launch_convt_to_conv1x1(const float* wt, float* out, int Cin, int Cout, cudaStream_t s) {
   convt_to_conv1x1_kernel<<<16 * Cout, 64, 0, s>>>(wt, out, Cin, Cout);
   DYF_LAUNCH_OK("convt_to_conv1x1_kernel");

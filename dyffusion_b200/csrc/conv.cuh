@@ -92,8 +92,8 @@ struct UpConvParams {
   int C[2], ld[2];              // channels taken from each source (multiples of 64; C[1] may be 0), channel strides
   int rows, H, W;               // low-res grid; the output is [rows, 2H, 2W, out_ld]
   int Cout;                     // output channels of the reference conv (multiple of 32); GEMM N = 4 * Cout
-  const __nv_bfloat16* w[5];    // composite weights as tcgen05 stage tiles: interior, first row, last row, first col, last col
-  const float* wc;              // corner composites, fp32 [4 corners][4 taps][Cin][4 * Cout]
+  const __nv_bfloat16* w[9];    // composite weights as tcgen05 stage tiles: interior, first row, last row, first col,
+                                // last col, corners (top-left, top-right, bottom-left, bottom-right)
   __nv_bfloat16* out;
   int out_ld;
   const float* tabA;            // [rows / tab_div, Cout] epilogue tables (as ConvParams)
@@ -104,9 +104,8 @@ struct UpConvParams {
 };
 bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W);
 size_t conv_up_weight_elems(int Cin, int Cout);
-size_t conv_up_corner_floats(int Cin, int Cout);
-int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* w_corner, float* scratch,
-                      cudaStream_t s);
+#define DYF_UP_VARIANTS 9
+int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* scratch, cudaStream_t s);
 int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
 
 int launch_conv_mma(const ConvParams& p, cudaStream_t stream);

@@ -37,7 +37,7 @@ constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each drainin
 __host__ __device__ constexpr int prod_warps(bool tma) { return tma ? 1 : 8; }
 __host__ __device__ constexpr int cta_threads(bool tma) { return (EPI_WARPS + prod_warps(tma) + 2) * 32; }
 
-enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2 };
+enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2, S2K2 = 3 };  // S2K2 (2x2 / stride 2 / pad 0) runs on the S1K1 kernel, see launch_s2k2
 
 template <int MODE, int T = 1> struct Geo;  // T = pixel tiles side by side per work item (gathered patches: stride-2 mode only)
 template <int T> struct Geo<S1K3, T> {
@@ -111,7 +111,8 @@ struct __align__(8) Barriers {
 template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
 __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
-                                                              const __grid_constant__ CUtensorMap tmap) {
+                                                              const __grid_constant__ CUtensorMap tmap,
+                                                              const __grid_constant__ CUtensorMap tmap2, int nch_split) {
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
   constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
@@ -267,9 +268,12 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
             mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
             const uint32_t bar = smem_u32(&bars->a_full[st]);
             mbar_expect_tx(bar, PIXT * 128);
+            // nch_split > 0: the K axis is the concatenation of two tensor views (chunks [0, nch_split) / the rest)
+            const bool second = nch_split > 0 && c >= nch_split;
+            const uint64_t tm = reinterpret_cast<uint64_t>(second ? &tmap2 : &tmap);
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                ::"r"(smem_u32(sA + st * A_STAGE)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * G::CH),
+                ::"r"(smem_u32(sA + st * A_STAGE)), "l"(tm), "r"((second ? c - nch_split : c) * G::CH),
                   "r"(G::in_x(ox0, 0)), "r"(G::in_y(oy0, 0)), "r"(row), "r"(bar) : "memory");
           }
         }
@@ -440,6 +444,8 @@ template <> struct Stages<S1K3, 64, false> { static constexpr int T = 1, GT = 3,
 template <> struct Stages<S1K3, 128, false> { static constexpr int T = 1, GT = 3, A = 3, B = 3; };
 template <> struct Stages<S1K1, 64, true> { static constexpr int T = 2, GT = 1, A = 5, B = 4; };
 template <> struct Stages<S1K1, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };
+template <> struct Stages<S1K1, 64, true, 1> { static constexpr int T = 1, GT = 1, A = 6, B = 6; };   // grids <= 8 pixels wide
+template <> struct Stages<S1K1, 128, true, 1> { static constexpr int T = 1, GT = 1, A = 6, B = 6; };
 template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
@@ -462,8 +468,9 @@ static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out
   return 0;
 }
 
+// views: optional pair of pre-built tensor maps splitting the K axis (2x2 / stride-2 layers); nch_split = chunks of the first
 template <int BN, int MODE, bool TMA, int V = 0>
-int launch_t(const ConvParams& p, cudaStream_t stream) {
+int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views = nullptr, int nch_split = 0) {
   using St = Stages<MODE, BN, TMA, V>;
   constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
   using G = Geo<MODE, TMA ? 1 : T>;
@@ -478,8 +485,9 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  CUtensorMap tmap{};
-  if (TMA && make_patch_tmap(p, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
+  CUtensorMap tmap{}, tmap2{};
+  if (views) { tmap = views[0]; tmap2 = views[1]; }
+  else if (TMA && make_patch_tmap(p, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
   const int tiles_x = (p.Wo + TILE_W * T - 1) / (TILE_W * T), tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
   const int n_tiles = (p.Cout + BN - 1) / BN;
   const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
@@ -489,7 +497,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
   conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
-                                                                                (int)work, tmap);
+                                                                                (int)work, tmap, tmap2, nch_split);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -498,6 +506,7 @@ int mode_of(int k, int stride, int pad) {
   if (k == 3 && stride == 1 && pad == 1) return S1K3;
   if (k == 4 && stride == 2 && pad == 1) return S2K4;
   if (k == 1 && stride == 1 && pad == 0) return S1K1;
+  if (k == 2 && stride == 2 && pad == 0) return S2K2;
   return -1;
 }
 
@@ -510,6 +519,7 @@ bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad) {
   const int mode = mode_of(k, stride, pad);
   if (mode < 0 || Cout % 8 != 0) return false;
   if (mode == S1K1) return Cin_pad % 64 == 0 && (Cout <= 64 || Cout % 128 == 0);
+  if (mode == S2K2) return Cin_pad % 32 == 0 && (Cout == 64 || Cout % 128 == 0);
   if (!(Cout == 64 || Cout % 128 == 0)) return false;
   return Cin_pad % (mode == S1K3 ? 64 : 32) == 0;
 }
@@ -519,8 +529,44 @@ bool conv_umma_eligible(const ConvParams& p) {
          p.out_fp32 == 0 && ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
 }
 
+// 2x2 / stride-2 / pad-0 conv = a 1x1 conv over the space-to-depth view of the input, and that view needs no copy: for
+// filter row ky, the NHWC tensor read with pixel pitch 2*Cin and row pitch 2*Wi*Cin from base + ky*Wi*Cin IS
+// [rows, Hi/2, Wi/2, (kx, ci)].  The K axis is the two views back to back: K index = (ky*2 + kx)*Cin + ci (weights are
+// staged in that order by launch_k2s2_to_conv1x1).
+static int launch_s2k2(const ConvParams& p, cudaStream_t stream) {
+  if ((p.Hi | p.Wi) & 1) return 0;
+  const bool n64 = umma_tile_n(p.Cout) == 64, small = p.Wo <= TILE_W;
+  const int bw = TILE_W * (small ? 1 : 2);
+  using Key = std::tuple<const void*, int, int, int, int, int>;
+  struct Pair { CUtensorMap m[2]; };
+  static std::map<Key, Pair> cache;
+  const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin, bw};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    Pair pr;
+    const cuuint64_t dims[4] = {(cuuint64_t)2 * p.Cin, (cuuint64_t)p.Wi / 2, (cuuint64_t)p.Hi / 2, (cuuint64_t)p.rows};
+    const cuuint64_t strides[3] = {(cuuint64_t)4 * p.Cin, (cuuint64_t)4 * p.Wi * p.Cin, (cuuint64_t)2 * p.Hi * p.Wi * p.Cin};
+    const cuuint32_t box[4] = {64, (cuuint32_t)bw, TILE_H, 1};
+    for (int ky = 0; ky < 2; ++ky)
+      if (make_tmap4(p.in + (size_t)ky * p.Wi * p.Cin, dims, strides, box, &pr.m[ky]) != 0) return 0;
+    if (cache.size() > 1024) cache.clear();
+    it = cache.emplace(key, pr).first;
+  }
+  ConvParams q = p;
+  q.Cin = 4 * p.Cin;       // K of the equivalent 1x1 conv
+  q.Cin_real = 4 * p.Cin_real;  // FLOP accounting (launch_t counts taps x Cin_real)
+  q.KH = q.KW = 1; q.stride = 1; q.pad = 0;
+  q.Hi = p.Ho; q.Wi = p.Wo;
+  const int split = 2 * p.Cin / 64;
+  int rc;
+  if (small) rc = n64 ? launch_t<64, S1K1, true, 1>(q, stream, it->second.m, split) : launch_t<128, S1K1, true, 1>(q, stream, it->second.m, split);
+  else rc = n64 ? launch_t<64, S1K1, true>(q, stream, it->second.m, split) : launch_t<128, S1K1, true>(q, stream, it->second.m, split);
+  return rc;
+}
+
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
+  if (mode_of(p.KH, p.stride, p.pad) == S2K2) return launch_s2k2(p, stream);
   const bool n64 = umma_tile_n(p.Cout) == 64;
   const int mode = mode_of(p.KH, p.stride, p.pad);
   static const char* env_a = getenv("DYF_UMMA_A");  // "cpasync" forces the cp.async patch gather

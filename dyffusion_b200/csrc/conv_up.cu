@@ -33,31 +33,39 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 1 + 1 + 1) * 32;    // epilogue + A producer + MMA + weight producer warps
 constexpr int B_TAP = BN * 64 * 2;                       // one tap of one 64-channel chunk: [k8][BN][8] bf16
 
-enum Kind { K_MAIN = 0, K_ROW = 1, K_COL = 2 };
+// Tile kinds.  A GEMM row group (8 rows = one 1024-byte swizzle atom of the patch) is
+//   MAIN    8 consecutive pixels of one image      (16 x 16-pixel super-tile = two 16 x 8 M-tiles per weight stage)
+//   ROW/COL 8 consecutive IMAGES at one pixel       (M-tile = 16 border pixels x 8 images: the patch is loaded through
+//           a tensor map whose dimension order is (C, image, W, H) resp. (C, image, H, W), so that small images fill the
+//           tile as well as large ones)
+//   CORNER  8 consecutive images at the corner pixel (M-tile = 128 images; only the 2 x 2 in-bounds taps are loaded)
+enum Kind { K_MAIN = 0, K_ROW = 1, K_COL = 2, K_CORNER = 3, N_KINDS = 4 };
 
 template <int KIND> struct UGeo;
-template <> struct UGeo<K_MAIN> {  // 16 x 16 low-res pixels = two 16 x 8 M-tiles sharing every weight stage
-  static constexpr int T = 2, NBOX = 1, BW = 18, BH = 18;
-  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = REGION;
-  static constexpr int SBO = BW * 128, AS = 2, BS = 8;
-  __device__ static constexpr int tap_off(int ty, int tx) { return (ty * BW + tx) * 128; }
+template <> struct UGeo<K_MAIN> {
+  static constexpr int T = 2, NTAP = 9, A_BYTES = 18 * 18 * 128, A_STAGE = ((A_BYTES + 1023) / 1024) * 1024;
+  static constexpr int SBO = 18 * 128, AS = 2, BS = 8;
+  __device__ static constexpr int tap_off(int t) { return ((t / 3) * 18 + t % 3) * 128; }
 };
-template <> struct UGeo<K_ROW> {   // 128 consecutive pixels of the first / last low-res row
-  static constexpr int T = 1, NBOX = 1, BW = 130, BH = 3;
-  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = REGION;
+template <> struct UGeo<K_ROW> {   // patch [3 rows][18 pixels][8 images] x 128 B
+  static constexpr int T = 1, NTAP = 9, A_BYTES = 3 * 18 * 8 * 128, A_STAGE = A_BYTES;
   static constexpr int SBO = 1024, AS = 2, BS = 7;
-  __device__ static constexpr int tap_off(int ty, int tx) { return (ty * BW + tx) * 128; }
+  __device__ static constexpr int tap_off(int t) { return ((t / 3) * 18 + t % 3) * 1024; }
 };
-template <> struct UGeo<K_COL> {   // 128 consecutive pixels of the first / last low-res column: one box per tap column
-  static constexpr int T = 1, NBOX = 3, BW = 1, BH = 130;
-  static constexpr int REGION = ((BW * BH * 128 + 1023) / 1024) * 1024, A_STAGE = NBOX * REGION;
+template <> struct UGeo<K_COL> {   // patch [3 columns][18 pixels][8 images] x 128 B
+  static constexpr int T = 1, NTAP = 9, A_BYTES = 3 * 18 * 8 * 128, A_STAGE = A_BYTES;
   static constexpr int SBO = 1024, AS = 2, BS = 7;
-  __device__ static constexpr int tap_off(int ty, int tx) { return tx * REGION + ty * 128; }
+  __device__ static constexpr int tap_off(int t) { return ((t % 3) * 18 + t / 3) * 1024; }
+};
+template <> struct UGeo<K_CORNER> {  // patch [2 rows][2 columns][128 images] x 128 B
+  static constexpr int T = 1, NTAP = 4, A_BYTES = 4 * 128 * 128, A_STAGE = A_BYTES;
+  static constexpr int SBO = 1024, AS = 2, BS = 5;
+  __device__ static constexpr int tap_off(int t) { return t * 128 * 128; }
 };
 
-// One launch runs the three tile kinds back to back as phases of the same persistent CTAs (a CTA that runs out of
-// MAIN tiles moves on to ROW / COL tiles without waiting for the others).  The barrier block and the epilogue tables sit
-// at a fixed offset behind the largest A/B ring; barriers are re-initialised between phases.
+// One launch runs the four tile kinds back to back as phases of the same persistent CTAs (a CTA that runs out of MAIN
+// tiles moves on to the border tiles without waiting for the others).  The barrier block and the epilogue tables sit at
+// a fixed offset behind the largest A/B ring; barriers are re-initialised between phases.
 constexpr int MAX_AS = 2, MAX_BS = 8;
 struct __align__(16) UBarriers {
   uint64_t a_full[MAX_AS], a_empty[MAX_AS], b_full[MAX_BS], b_empty[MAX_BS], acc_full[2], acc_empty[2];
@@ -65,11 +73,12 @@ struct __align__(16) UBarriers {
 };
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 template <int KIND> constexpr int ring_bytes() { return UGeo<KIND>::AS * UGeo<KIND>::A_STAGE + UGeo<KIND>::BS * B_TAP; }
-constexpr int BAR_OFF = cmax(ring_bytes<K_MAIN>(), cmax(ring_bytes<K_ROW>(), ring_bytes<K_COL>()));
+constexpr int BAR_OFF = cmax(cmax(ring_bytes<K_MAIN>(), ring_bytes<K_ROW>()), cmax(ring_bytes<K_COL>(), ring_bytes<K_CORNER>()));
 constexpr int TAB_OFF = BAR_OFF + (((int)sizeof(UBarriers) + 15) & ~15);
 constexpr int SMEM_BYTES = TAB_OFF + 4 * BN * 4 + 64;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
-struct UpWork { int tiles_a[3], num_work[3]; };  // per kind: tile blocks along the tiled axis, work items
+struct UpWork { int tiles_a[N_KINDS], num_work[N_KINDS]; };  // per kind: tile blocks along the tiled axis, work items
+struct UpMaps { CUtensorMap m[N_KINDS][2]; };                // per kind, per source
 
 // Fused epilogue of NG groups of 8 consecutive GEMM columns starting at column n (each group = one parity class, channels
 // co..co+7) of low-res pixel (i, j).  tA / tB point at the table entries of column n (global memory, or the per-item copy
@@ -114,20 +123,20 @@ __device__ __forceinline__ void up_store(const UpConvParams& p, int img, int i, 
 
 template <int KIND>
 __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, uint32_t tmem_base, int tiles_a, int n_tiles,
-                                         int num_work, const CUtensorMap* tmap0, const CUtensorMap* tmap1) {
+                                         int num_work, int first, const CUtensorMap* tmap0, const CUtensorMap* tmap1) {
   using G = UGeo<KIND>;
-  constexpr int AS = G::AS, BS = G::BS, T = G::T, A_STAGE = G::A_STAGE;
+  constexpr int AS = G::AS, BS = G::BS, T = G::T, A_STAGE = G::A_STAGE, NTAP = G::NTAP;
   static_assert(AS <= MAX_AS && BS <= MAX_BS, "barrier block too small");
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS * A_STAGE;
   UBarriers* bars = reinterpret_cast<UBarriers*>(smem + BAR_OFF);
-  float* sTab = reinterpret_cast<float*>(smem + TAB_OFF);  // [2 acc][A | B][BN] epilogue tables
+  float* sTab = reinterpret_cast<float*>(smem + TAB_OFF);  // [2 acc][A | B][BN] epilogue tables (MAIN tiles)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nch0 = p.C[0] >> 6, nchunks = (p.C[0] + p.C[1]) >> 6;
 
-  // work item -> (n_tile, image, side | tile origin).  MAIN: tiles_a = tiles_x (16-pixel blocks per row); ROW / COL:
-  // tiles_a = 128-pixel blocks along the border, `side` 0 = first row / column, 1 = last.
+  // work item -> (n_tile, first image, pixel origin, side).  tiles_a = 16-pixel blocks along the tiled axis; `side`:
+  // ROW / COL 0 = first row / column, 1 = last; CORNER bit 1 = bottom, bit 0 = right.
   auto decode = [&](int w, int& n_tile, int& img, int& i0, int& j0, int& side) {
     n_tile = w % n_tiles;
     int t = w / n_tiles;
@@ -139,12 +148,16 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
       i0 = ty * 16;
       j0 = (t - ty * tiles_a) * 16;
       side = 0;
+    } else if constexpr (KIND == K_CORNER) {
+      side = t & 3;
+      img = (t >> 2) * 128;
+      i0 = (side & 2) ? p.H - 1 : 0;
+      j0 = (side & 1) ? p.W - 1 : 0;
     } else {
-      const int per_img = 2 * tiles_a;
-      img = t / per_img;
-      t -= img * per_img;
-      side = t / tiles_a;
-      const int blk = (t - side * tiles_a) * 128;
+      const int blk = (t % tiles_a) * 16;
+      t /= tiles_a;
+      side = t & 1;
+      img = (t >> 1) * 8;
       if constexpr (KIND == K_ROW) { i0 = side ? p.H - 1 : 0; j0 = blk; }
       else { j0 = side ? p.W - 1 : 0; i0 = blk; }
     }
@@ -156,33 +169,37 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
     const int quarter = warp & 3, m_local = quarter * 32 + lane;
     constexpr int COLS = BN / (EPI_WARPS / 4);
     const int cbeg = (warp >> 2) * COLS;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    for (int w = first; w < num_work; w += gridDim.x, ++it) {
       int n_tile, img, i0, j0, side;
       decode(w, n_tile, img, i0, j0, side);
       const int acc = it & 1;
-      float* const tA = sTab + acc * 2 * BN;  // this item's epilogue tables, staged once in shared memory
-      float* const tB = tA + BN;
-      if (tid < BN) {
-        const size_t off = (size_t)(img / p.tab_div) * p.Cout + (n_tile * BN + tid) % p.Cout;
-        tA[tid] = __ldg(p.tabA + off);
-        tB[tid] = __ldg(p.tabB + off);
+      float* const sA_tab = sTab + acc * 2 * BN;
+      if constexpr (KIND == K_MAIN) {  // one image per item: stage its epilogue tables once in shared memory
+        if (tid < BN) {
+          const size_t off = (size_t)(img / p.tab_div) * p.Cout + (n_tile * BN + tid) % p.Cout;
+          sA_tab[tid] = __ldg(p.tabA + off);
+          sA_tab[BN + tid] = __ldg(p.tabB + off);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int tile = 0; tile < T; ++tile) {
-        int i, j;
+        int im, i, j;
         bool valid;
         if constexpr (KIND == K_MAIN) {
-          i = i0 + (m_local >> 3); j = j0 + tile * 8 + (m_local & 7);
+          im = img; i = i0 + (m_local >> 3); j = j0 + tile * 8 + (m_local & 7);
           valid = i >= 1 && i <= p.H - 2 && j >= 1 && j <= p.W - 2;
         } else if constexpr (KIND == K_ROW) {
-          i = i0; j = j0 + m_local;
-          valid = j >= 1 && j <= p.W - 2;
+          im = img + (m_local & 7); i = i0; j = j0 + (m_local >> 3);
+          valid = im < p.rows && j >= 1 && j <= p.W - 2;
+        } else if constexpr (KIND == K_COL) {
+          im = img + (m_local & 7); j = j0; i = i0 + (m_local >> 3);
+          valid = im < p.rows && i >= 1 && i <= p.H - 2;
         } else {
-          j = j0; i = i0 + m_local;
-          valid = i >= 1 && i <= p.H - 2;
+          im = img + m_local; i = i0; j = j0;
+          valid = im < p.rows;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
 #pragma unroll 1
@@ -194,7 +211,13 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
             float y[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) y[e] = __uint_as_float(v[e]);
-            up_store<4>(p, img, i, j, n_tile * BN + cg, y, tA + cg, tB + cg);
+            const int n = n_tile * BN + cg;
+            if constexpr (KIND == K_MAIN) {
+              up_store<4>(p, im, i, j, n, y, sA_tab + cg, sA_tab + BN + cg);
+            } else {  // several images per tile: tables straight from global memory (32 columns = one class: contiguous)
+              const size_t off = (size_t)(im / p.tab_div) * p.Cout + n % p.Cout;
+              up_store<4>(p, im, i, j, n, y, p.tabA + off, p.tabB + off);
+            }
           }
         }
       }
@@ -202,26 +225,28 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
       mbar_arrive(smem_u32(&bars->acc_empty[acc]));
     }
   } else if (warp == EPI_WARPS) {
-    // =============================== A producer: TMA boxes of the low-res [x | skip] patch =========================
+    // =============================== A producer: one TMA box of the low-res [x | skip] patch per chunk ==============
     if (lane == 0) {
       int ca = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = first; w < num_work; w += gridDim.x) {
         int n_tile, img, i0, j0, side;
         decode(w, n_tile, img, i0, j0, side);
+        // box origin in the coordinate order of this kind's tensor map (after the channel coordinate)
+        int c1, c2, c3;
+        if constexpr (KIND == K_MAIN) { c1 = j0 - 1; c2 = i0 - 1; c3 = img; }                 // (C, W, H, image)
+        else if constexpr (KIND == K_ROW) { c1 = img; c2 = j0 - 1; c3 = i0 - 1; }               // (C, image, W, H)
+        else if constexpr (KIND == K_COL) { c1 = img; c2 = i0 - 1; c3 = j0 - 1; }               // (C, image, H, W)
+        else { c1 = img; c2 = (side & 1) ? p.W - 2 : 0; c3 = (side & 2) ? p.H - 2 : 0; }        // (C, image, W, H), 2 x 2 box
         for (int c = 0; c < nchunks; ++c, ++ca) {
           const int st = ca % AS;
           mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
           const uint32_t bar = smem_u32(&bars->a_full[st]);
-          mbar_expect_tx(bar, G::NBOX * G::BW * G::BH * 128);
+          mbar_expect_tx(bar, G::A_BYTES);
           const uint64_t tm = reinterpret_cast<uint64_t>(c < nch0 ? tmap0 : tmap1);
           const int cc = (c < nch0 ? c : c - nch0) * 64;
-#pragma unroll
-          for (int b = 0; b < G::NBOX; ++b) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                ::"r"(smem_u32(sA + st * A_STAGE + b * G::REGION)), "l"(tm), "r"(cc), "r"(j0 - 1 + b), "r"(i0 - 1), "r"(img),
-                  "r"(bar) : "memory");
-          }
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(smem_u32(sA + st * A_STAGE)), "l"(tm), "r"(cc), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
         }
       }
     }
@@ -237,7 +262,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
     const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
     constexpr int AK = 32 >> 4, BK = (2 * BN * 16) >> 4;
     int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    for (int w = first; w < num_work; w += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -247,11 +272,11 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
         tc_fence_after();
         const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (A_STAGE >> 4));
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < NTAP; ++tap) {
           mbar_wait(bar_b_full + sb * 8, pb);
           tc_fence_after();
           const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_TAP >> 4));
-          const int a_off = G::tap_off(tap / 3, tap % 3);
+          const int a_off = G::tap_off(tap);
 #pragma unroll
           for (int tile = 0; tile < T; ++tile)
             umma_tap<4, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * 8 * 128) >> 4), b_st, idesc,
@@ -267,18 +292,22 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
   } else {
     // =============================== B producer: one bulk-TMA copy per (chunk, tap) weight tile ====================
     if (lane == 0) {
-      const int per_tile = nchunks * 9;
       int sb = 0, pb = 1;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = first; w < num_work; w += gridDim.x) {
         int n_tile, img, i0, j0, side;
         decode(w, n_tile, img, i0, j0, side);
-        const __nv_bfloat16* wv = KIND == K_MAIN ? p.w[0] : KIND == K_ROW ? p.w[1 + side] : p.w[3 + side];
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(wv) + (size_t)n_tile * per_tile * B_TAP;
-        for (int i = 0; i < per_tile; ++i) {
-          mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
-          mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_TAP);
-          bulk_g2s(smem_u32(sB + sb * B_TAP), src + (size_t)i * B_TAP, B_TAP, smem_u32(&bars->b_full[sb]));
-          if (++sb == BS) { sb = 0; pb ^= 1; }
+        const __nv_bfloat16* wv = KIND == K_MAIN ? p.w[0] : KIND == K_ROW ? p.w[1 + side] : KIND == K_COL ? p.w[3 + side] : p.w[5 + side];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wv) + (size_t)n_tile * nchunks * 9 * B_TAP;
+        for (int c = 0; c < nchunks; ++c) {
+#pragma unroll 1
+          for (int t = 0; t < NTAP; ++t) {
+            // CORNER: box tap (by, bx) is tap (by + !bottom, bx + !right) of the 3 x 3 composite
+            const int tap9 = KIND == K_CORNER ? ((t >> 1) + ((side & 2) ? 0 : 1)) * 3 + (t & 1) + ((side & 1) ? 0 : 1) : t;
+            mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
+            mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_TAP);
+            bulk_g2s(smem_u32(sB + sb * B_TAP), src + (size_t)(c * 9 + tap9) * B_TAP, B_TAP, smem_u32(&bars->b_full[sb]));
+            if (++sb == BS) { sb = 0; pb ^= 1; }
+          }
         }
       }
     }
@@ -286,12 +315,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
 }
 
 __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams p, const UpWork wk, int n_tiles,
-                                                             const __grid_constant__ CUtensorMap tm_main0,
-                                                             const __grid_constant__ CUtensorMap tm_main1,
-                                                             const __grid_constant__ CUtensorMap tm_row0,
-                                                             const __grid_constant__ CUtensorMap tm_row1,
-                                                             const __grid_constant__ CUtensorMap tm_col0,
-                                                             const __grid_constant__ CUtensorMap tm_col1) {
+                                                             const __grid_constant__ UpMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   UBarriers* bars = reinterpret_cast<UBarriers*>(smem + BAR_OFF);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -299,8 +323,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  unsigned done = 0;  // work items of the earlier phases
 #pragma unroll 1
-  for (int phase = 0; phase < 3; ++phase) {
+  for (int phase = 0; phase < N_KINDS; ++phase) {
     if (tid == 0) {
       for (int i = 0; i < MAX_AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), 1); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
       for (int i = 0; i < MAX_BS; ++i) { mbar_init(smem_u32(&bars->b_full[i]), 1); mbar_init(smem_u32(&bars->b_empty[i]), 1); }
@@ -311,80 +336,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    if (phase == 0) up_phase<K_MAIN>(p, smem, tmem_base, wk.tiles_a[0], n_tiles, wk.num_work[0], &tm_main0, &tm_main1);
-    else if (phase == 1) up_phase<K_ROW>(p, smem, tmem_base, wk.tiles_a[1], n_tiles, wk.num_work[1], &tm_row0, &tm_row1);
-    else up_phase<K_COL>(p, smem, tmem_base, wk.tiles_a[2], n_tiles, wk.num_work[2], &tm_col0, &tm_col1);
+    const CUtensorMap* m0 = &maps.m[phase][0];
+    const CUtensorMap* m1 = &maps.m[phase][1];
+    // the work items of all phases form one round-robin sequence over the CTAs: a phase starts at the CTA after the one
+    // that took the previous phase's last item, so CTAs with one MAIN tile less pick up the border tiles first
+    const int first = (int)((blockIdx.x + gridDim.x - done % gridDim.x) % gridDim.x);
+    if (phase == K_MAIN) up_phase<K_MAIN>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);
+    else if (phase == K_ROW) up_phase<K_ROW>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);
+    else if (phase == K_COL) up_phase<K_COL>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);
+    else up_phase<K_CORNER>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);
+    done += (unsigned)wk.num_work[phase];
     tc_fence_before();
     __syncthreads();  // every role of this CTA has drained the phase: barriers can be re-initialised
   }
   if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(bars->tmem_base), "r"(512));
-  }
-}
-
-// The four corner pixels of every image (2 x 2 in-bounds taps each): CUDA cores, fp32 composite weights
-// wc[corner][tap][Cin][4*Cout].  One block = one corner x 8 images x 256 GEMM columns: lanes own 8 consecutive columns
-// (coalesced weight rows), the 8 warps split the 4*Cin reduction and combine through shared memory in a fixed order.
-constexpr int CORNER_IMGS = 8;
-__global__ void __launch_bounds__(256) conv_up_corner_kernel(const UpConvParams p) {
-  extern __shared__ float sx[];  // [img][tap][Cin] inputs, then [slice][img][lane][8] partial sums
-  const int corner = blockIdx.x, img0 = blockIdx.y * CORNER_IMGS;
-  const int Cin = p.C[0] + p.C[1], N = 4 * p.Cout, K = 4 * Cin;
-  const int bottom = corner >> 1, right = corner & 1;
-  const int i = bottom ? p.H - 1 : 0, j = right ? p.W - 1 : 0;
-  const int nimg = min(CORNER_IMGS, p.rows - img0);
-  for (int e8 = threadIdx.x; e8 < CORNER_IMGS * K / 8; e8 += blockDim.x) {  // 8 channels (one 128-bit load) per step
-    const int e = e8 * 8, c = e % Cin, t = (e / Cin) & 3, im = e / K;
-    const int ii = i + (t >> 1) - bottom, jj = j + (t & 1) - right;  // taps (di, dj) in {0,1}^2 (top/left) or {-1,0}^2
-    const int s = c < p.C[0] ? 0 : 1, cs = s ? c - p.C[0] : c;
-    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (im < nimg)
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.src[s] + (((size_t)(img0 + im) * p.H + ii) * p.W + jj) * p.ld[s] + cs)), f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sx[e + k] = f[k];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int n0 = (blockIdx.z * 32 + lane) * 8;
-  float* red = sx + CORNER_IMGS * K;
-  float acc[CORNER_IMGS][8];
-#pragma unroll
-  for (int im = 0; im < CORNER_IMGS; ++im)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[im][e] = 0.f;
-  if (n0 < N) {
-    const float* wc = p.wc + (size_t)corner * K * N + n0;
-    const int per = K / 8;
-#pragma unroll 8
-    for (int tc = slice * per; tc < (slice + 1) * per; ++tc) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (size_t)tc * N) + 1);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int im = 0; im < CORNER_IMGS; ++im) {
-        const float x = sx[im * K + tc];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[im][e] = fmaf(x, wv[e], acc[im][e]);
-      }
-    }
-  }
-#pragma unroll
-  for (int im = 0; im < CORNER_IMGS; ++im)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) red[((slice * CORNER_IMGS + im) * 32 + lane) * 8 + e] = acc[im][e];
-  __syncthreads();
-  const int im = slice;  // warp `slice` finishes image `slice`
-  if (n0 < N && im < nimg) {
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = 0.f;
-#pragma unroll
-      for (int sl = 0; sl < 8; ++sl) v += red[((sl * CORNER_IMGS + im) * 32 + lane) * 8 + e];
-      y[e] = v;
-    }
-    const size_t toff = (size_t)((img0 + im) / p.tab_div) * p.Cout + n0 % p.Cout;
-    up_store<1>(p, img0 + im, i, j, n0, y, p.tabA + toff, p.tabB + toff);
   }
 }
 
@@ -411,16 +377,6 @@ __global__ void __launch_bounds__(256) compose_up_kernel(const float* __restrict
       out[((size_t)n * Cin + ci) * 9 + di * 3 + dj] = s;
     }
 }
-// corner layout: wc[tap = tdi*2 + tdj][ci][n] from a composed variant [n][ci][3][3]; (di, dj) = (tdi, tdj) - (bottom, right)
-__global__ void __launch_bounds__(256) corner_layout_kernel(const float* __restrict__ comp, float* __restrict__ wc, int N,
-                                                           int Cin, int bottom, int right) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)4 * Cin * N) return;
-  const int n = (int)(idx % N), ci = (int)((idx / N) % Cin), t = (int)(idx / ((long long)N * Cin));
-  const int di = (t >> 1) - bottom + 1, dj = (t & 1) - right + 1;  // index into the 3 x 3 composite taps
-  wc[idx] = comp[((size_t)n * Cin + ci) * 9 + di * 3 + dj];
-}
-
 // 1-D composite maps by simulating the reference ops on basis vectors: M[a][d][k] = coefficient of w[k] * x[i + d - 1]
 // in output 2i + a of (zero-padded 3-tap conv) o (clamped bilinear x2), for i at the start / interior / end of the axis.
 void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
@@ -440,51 +396,30 @@ void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
       }
 }
 
-int launch_phases(const UpConvParams& p, cudaStream_t stream) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    DYF_CUDA_OK(cudaGetDevice(&dev));
-    DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  }
-  using Key = std::tuple<const void*, int, int, int, int, int, int>;
-  static std::map<Key, CUtensorMap> cache;
-  const int bw[3] = {UGeo<K_MAIN>::BW, UGeo<K_ROW>::BW, UGeo<K_COL>::BW};
-  const int bh[3] = {UGeo<K_MAIN>::BH, UGeo<K_ROW>::BH, UGeo<K_COL>::BH};
-  CUtensorMap tm[3][2];
-  for (int k = 0; k < 3; ++k)
-    for (int s = 0; s < 2; ++s) {
-      const int sidx = p.C[s] ? s : 0;  // single-source layers: the second map is never used
-      const Key key{p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], k};
-      auto it = cache.find(key);
-      if (it == cache.end()) {
-        CUtensorMap m;
-        if (make_nhwc_tmap(p.src[sidx], p.rows, p.H, p.W, p.C[sidx], p.ld[sidx], bw[k], bh[k], 1, &m) != 0) {
-          set_error("conv_up: cuTensorMapEncodeTiled failed");
-          return -1;
-        }
-        if (cache.size() > 4096) cache.clear();
-        it = cache.emplace(key, m).first;
-      }
-      tm[k][s] = it->second;
+// Tensor maps of one source for the four tile kinds (cached per buffer / geometry: the workspace carving is stable).
+int source_maps(const UpConvParams& p, int s, CUtensorMap out[N_KINDS]) {
+  using Key = std::tuple<const void*, int, int, int, int, int>;
+  struct Entry { CUtensorMap m[N_KINDS]; };
+  static std::map<Key, Entry> cache;
+  const Key key{p.src[s], p.rows, p.H, p.W, p.C[s], p.ld[s]};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    Entry e;
+    const cuuint64_t C = (cuuint64_t)p.C[s], N = (cuuint64_t)p.rows, W = (cuuint64_t)p.W, H = (cuuint64_t)p.H;
+    const cuuint64_t pix = (cuuint64_t)p.ld[s] * 2, row = W * pix, img = H * row;
+    const cuuint64_t d_main[4] = {C, W, H, N}, s_main[3] = {pix, row, img};
+    const cuuint64_t d_row[4] = {C, N, W, H}, s_row[3] = {img, pix, row};
+    const cuuint64_t d_col[4] = {C, N, H, W}, s_col[3] = {img, row, pix};
+    const cuuint32_t b_main[4] = {64, 18, 18, 1}, b_edge[4] = {64, 8, 18, 3}, b_corner[4] = {64, 128, 2, 2};
+    if (make_tmap4(p.src[s], d_main, s_main, b_main, &e.m[K_MAIN]) || make_tmap4(p.src[s], d_row, s_row, b_edge, &e.m[K_ROW]) ||
+        make_tmap4(p.src[s], d_col, s_col, b_edge, &e.m[K_COL]) || make_tmap4(p.src[s], d_row, s_row, b_corner, &e.m[K_CORNER])) {
+      set_error("conv_up: cuTensorMapEncodeTiled failed");
+      return -1;
     }
-  const int n_tiles = 4 * p.Cout / BN;
-  UpWork wk;
-  wk.tiles_a[0] = (p.W + 15) / 16; wk.tiles_a[1] = (p.W + 127) / 128; wk.tiles_a[2] = (p.H + 127) / 128;
-  const long long work[3] = {(long long)wk.tiles_a[0] * ((p.H + 15) / 16) * p.rows * n_tiles,
-                             (long long)2 * wk.tiles_a[1] * p.rows * n_tiles, (long long)2 * wk.tiles_a[2] * p.rows * n_tiles};
-  for (int k = 0; k < 3; ++k) {
-    if (work[k] > 0x7fffffffLL) { set_error("conv_up: too many tiles"); return -1; }
-    wk.num_work[k] = (int)work[k];
+    if (cache.size() > 1024) cache.clear();
+    it = cache.emplace(key, e).first;
   }
-  const int grid = (int)(work[0] < num_sms ? work[0] : num_sms);
-  const int Cin = p.C[0] + p.C[1];
-  const double flops = 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin;  // = the reference conv on the upsampled grid
-  const double bytes = 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin);
-  ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_up_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p, wk, n_tiles, tm[0][0], tm[0][1], tm[1][0], tm[1][1], tm[2][0], tm[2][1]);
-  DYF_LAUNCH_OK("conv_up_kernel");
+  for (int k = 0; k < N_KINDS; ++k) out[k] = it->second.m[k];
   return 0;
 }
 
@@ -493,37 +428,24 @@ int launch_phases(const UpConvParams& p, cudaStream_t stream) {
 bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W) {
   return C0 > 0 && C0 % 64 == 0 && C1 % 64 == 0 && Cout % 32 == 0 && H >= 16 && W >= 16;
 }
-size_t conv_up_weight_elems(int Cin, int Cout) { return (size_t)4 * Cout * Cin * 9; }      // per UMMA variant (bf16)
-size_t conv_up_corner_floats(int Cin, int Cout) { return (size_t)4 * 4 * Cin * 4 * Cout; }  // all four corners (fp32)
+size_t conv_up_weight_elems(int Cin, int Cout) { return (size_t)4 * Cout * Cin * 9; }  // per variant (bf16 stage tiles)
 
-// w: conv weight fp32 [Cout, Cin, 3, 3].  Fills the five UMMA variants (interior, top, bottom, left, right) and the
-// corner table.  `scratch` must hold 4*Cout*Cin*9 floats.
-int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* w_corner, float* scratch,
-                      cudaStream_t s) {
+// w: conv weight fp32 [Cout, Cin, 3, 3].  Fills the nine composite variants as tcgen05 stage tiles: interior, first row,
+// last row, first column, last column, then the corners (top-left, top-right, bottom-left, bottom-right).
+// `scratch` must hold 4*Cout*Cin*9 floats.
+int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* scratch, cudaStream_t s) {
   float ax[3][2][3][3];
   for (int k = 0; k < 3; ++k) axis_maps(k, ax[k]);
   const long long total = (long long)4 * Cout * Cin;
-  auto compose = [&](int vk, int hk) {
+  const int vks[DYF_UP_VARIANTS] = {1, 0, 2, 1, 1, 0, 0, 2, 2}, hks[DYF_UP_VARIANTS] = {1, 1, 1, 0, 2, 0, 2, 0, 2};
+  for (int v = 0; v < DYF_UP_VARIANTS; ++v) {
     Maps m;
-    memcpy(m.V, ax[vk], sizeof(m.V));
-    memcpy(m.H, ax[hk], sizeof(m.H));
+    memcpy(m.V, ax[vks[v]], sizeof(m.V));
+    memcpy(m.H, ax[hks[v]], sizeof(m.H));
     compose_up_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, scratch, Cout, Cin, m);
-  };
-  const int vks[5] = {1, 0, 2, 1, 1}, hks[5] = {1, 1, 1, 0, 2};
-  for (int v = 0; v < 5; ++v) {
-    compose(vks[v], hks[v]);
     DYF_LAUNCH_OK("compose_up_kernel");
     int rc = launch_repack_umma(scratch, w_variants[v], 4 * Cout, Cin, 3, 1, 1, 0, s);
     if (rc) return rc;
-  }
-  const int N = 4 * Cout;
-  for (int corner = 0; corner < 4; ++corner) {
-    const int bottom = corner >> 1, right = corner & 1;
-    compose(bottom ? 2 : 0, right ? 2 : 0);
-    DYF_LAUNCH_OK("compose_up_kernel");
-    corner_layout_kernel<<<cdiv((long long)4 * Cin * N, 256), 256, 0, s>>>(scratch, w_corner + (size_t)corner * 4 * Cin * N, N,
-                                                                         Cin, bottom, right);
-    DYF_LAUNCH_OK("corner_layout_kernel");
   }
   return 0;
 }
@@ -533,19 +455,36 @@ int launch_conv_up(const UpConvParams& p, cudaStream_t stream) {
     set_error("conv_up: unsupported shape");
     return -1;
   }
-  int rc = launch_phases(p, stream);
-  if (rc) return rc;
-  const int Cin = p.C[0] + p.C[1];
-  const size_t smem = ((size_t)CORNER_IMGS * 4 * Cin + 8 * CORNER_IMGS * 32 * 8) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_corner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DYF_CUDA_OK(cudaGetDevice(&dev));
+    DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
-  dim3 grid(4, cdiv(p.rows, CORNER_IMGS), cdiv(4 * p.Cout, 32 * 8));
-  ProfScope prof(stream, KC_CONV_UMMA);
-  conv_up_corner_kernel<<<grid, 256, smem, stream>>>(p);
-  DYF_LAUNCH_OK("conv_up_corner_kernel");
+  UpMaps maps;
+  CUtensorMap tm[2][N_KINDS];
+  for (int s = 0; s < 2; ++s)
+    if (source_maps(p, p.C[s] ? s : 0, tm[s])) return -1;  // single-source layers: the second map is never used
+  for (int k = 0; k < N_KINDS; ++k) { maps.m[k][0] = tm[0][k]; maps.m[k][1] = tm[1][k]; }
+  const int n_tiles = 4 * p.Cout / BN;
+  UpWork wk;
+  wk.tiles_a[K_MAIN] = (p.W + 15) / 16; wk.tiles_a[K_ROW] = (p.W + 15) / 16; wk.tiles_a[K_COL] = (p.H + 15) / 16; wk.tiles_a[K_CORNER] = 1;
+  const long long work[N_KINDS] = {(long long)wk.tiles_a[K_MAIN] * ((p.H + 15) / 16) * p.rows * n_tiles,
+                                   (long long)2 * wk.tiles_a[K_ROW] * ((p.rows + 7) / 8) * n_tiles,
+                                   (long long)2 * wk.tiles_a[K_COL] * ((p.rows + 7) / 8) * n_tiles,
+                                   (long long)4 * ((p.rows + 127) / 128) * n_tiles};
+  for (int k = 0; k < N_KINDS; ++k) {
+    if (work[k] > 0x7fffffffLL) { set_error("conv_up: too many tiles"); return -1; }
+    wk.num_work[k] = (int)work[k];
+  }
+  const int grid = (int)(work[0] < num_sms ? work[0] : num_sms);
+  const int Cin = p.C[0] + p.C[1];
+  const double flops = 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin;  // = the reference conv on the upsampled grid
+  const double bytes = 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin);
+  ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
+  conv_up_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p, wk, n_tiles, maps);
+  DYF_LAUNCH_OK("conv_up_kernel");
   return 0;
 }
 

@@ -33,8 +33,7 @@ struct ConvLayer {
   int flops_cin = 0;                            // channels to count per tap in FLOP accounting (0 = Cin)
   int comp_wi = -1, comp_bi = -1, comp_cm = 0;  // composite layer: preceded by a folded 1x1 conv (weights, bias, width)
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
-  long long up_off[5] = {-1, -1, -1, -1, -1}; // fused upsample+conv: composite weight variants in Net::wq_umma
-  long long upc_off = -1;                     //   ... and the corner composites in Net::w_corner (floats)
+  long long up_off[DYF_UP_VARIANTS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // fused upsample+conv: composite variants in wq_umma
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
   int table = -1;                             // index into Net::time_layers
 };
@@ -90,11 +89,13 @@ struct Net {
   float* packed = nullptr;             // device: all fp32 params + folded vectors
   __nv_bfloat16* wq = nullptr;         // device: packed bf16 conv weights
   __nv_bfloat16* wq_umma = nullptr;    // device: weights of tcgen05-eligible layers as UMMA stage tiles
-  float* w_corner = nullptr;           // device: corner composites of the fused upsample+conv layers
-  size_t wc_floats = 0;
   TimeLayer* d_time_layers = nullptr;  // device copy
   bool finalized = false;
   int Hin = 0, Win = 0;                // network grid (after the optional outer resize)
+  // epilogue tables of time tuples seen before (the sampler's schedule is fixed, so every tuple recurs on every call):
+  // key = the times of one forward's logical calls, value = device buffer [tabA | tabB | scratch]
+  std::map<std::vector<float>, float*> tab_cache;
+  void clear_tab_cache();
 
   ~Net();
   int add_param(const std::string& key, std::vector<int64_t> shape, bool ignored = false);
@@ -113,7 +114,8 @@ struct Net {
   size_t workspace_bytes(int rows) const;
   int forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
               const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s,
-              int noise_src = -1, float noise_w = 0.f, int src_rows = 0, int group_rows = 1);
+              int noise_src = -1, float noise_w = 0.f, int src_rows = 0, int group_rows = 1,
+              const float* host_times = nullptr);  // host copy of `time` (rows / group_rows values): enables the table cache
 };
 
 struct Sampler {

@@ -14,8 +14,13 @@ Net::~Net() {
   if (packed) cudaFree(packed);
   if (wq) cudaFree(wq);
   if (wq_umma) cudaFree(wq_umma);
-  if (w_corner) cudaFree(w_corner);
   if (d_time_layers) cudaFree(d_time_layers);
+  clear_tab_cache();
+}
+
+void Net::clear_tab_cache() {
+  for (auto& kv : tab_cache) cudaFree(kv.second);
+  tab_cache.clear();
 }
 
 int Net::add_param(const std::string& key, std::vector<int64_t> shape, bool ignored) {
@@ -248,7 +253,7 @@ int Net::build_unet_simple() {
     // 3x3 decoder blocks on large grids run as ONE kernel: upsample + concat + conv as a composite conv on the low-res
     // grid (conv_up.cu).  Small grids keep the two-kernel path (their border tiles would dominate).
     const char* env_min = getenv("DYF_UPFUSE_MIN");  // smallest upsampled grid side that takes the fused kernel
-    const int fuse_min = env_min ? atoi(env_min) : 128;
+    const int fuse_min = env_min ? atoi(env_min) : 128;  // measured: below 128 the border phases + wave quantisation eat the gain
     const bool fuse_up = dec_k[i] == 3 && std::min(H, W) >= fuse_min && conv_up_shape_ok(c0, c1, dec_out[i], H / 2, W / 2) &&
                          !getenv("DYF_DISABLE_UPFUSE");
     int up = BUF_NONE;
@@ -266,9 +271,7 @@ int Net::build_unet_simple() {
     Op o{}; o.type = fuse_up ? OP_CONV_UP : OP_CONV; o.in0 = fuse_up ? x : up; o.in1 = fuse_up ? skip : BUF_NONE; o.out = y;
     o.c0 = c0; o.c1 = c1; o.layer = li; o.act = ACT_RELU; o.drop_p = d.dropout; o.site = site++;
     if (fuse_up) {
-      for (int v = 0; v < 5; ++v) { convs[li].up_off[v] = (long long)wu_elems; wu_elems += conv_up_weight_elems(c0 + c1, dec_out[i]); }
-      convs[li].upc_off = (long long)wc_floats;
-      wc_floats += conv_up_corner_floats(c0 + c1, dec_out[i]);
+      for (int v = 0; v < DYF_UP_VARIANTS; ++v) { convs[li].up_off[v] = (long long)wu_elems; wu_elems += conv_up_weight_elems(c0 + c1, dec_out[i]); }
     }
     ops.push_back(o);
     x = y;
@@ -508,14 +511,13 @@ int Net::finalize(cudaStream_t s) {
     if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
   if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
   if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
-  if (!w_corner && wc_floats) DYF_CUDA_OK(cudaMalloc(&w_corner, wc_floats * sizeof(float)));
   for (auto& c : convs) {
-    if (c.upc_off >= 0) {  // fused upsample + conv: composite weight variants (conv_up.cu)
+    if (c.up_off[0] >= 0) {  // fused upsample + conv: composite weight variants (conv_up.cu)
       float* scratch = nullptr;
       DYF_CUDA_OK(cudaMalloc(&scratch, conv_up_weight_elems(c.Cin, c.Cout) * sizeof(float)));
-      __nv_bfloat16* variants[5];
-      for (int v = 0; v < 5; ++v) variants[v] = wq_umma + c.up_off[v];
-      int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, w_corner + c.upc_off, scratch, s);
+      __nv_bfloat16* variants[DYF_UP_VARIANTS];
+      for (int v = 0; v < DYF_UP_VARIANTS; ++v) variants[v] = wq_umma + c.up_off[v];
+      int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, scratch, s);
       if (ru) return ru;
       DYF_CUDA_OK(cudaStreamSynchronize(s));
       DYF_CUDA_OK(cudaFree(scratch));
@@ -541,7 +543,15 @@ int Net::finalize(cudaStream_t s) {
       if (rcc) return rcc;
       w_src = composed;
     }
-    if (c.wu_off >= 0) {
+    if (c.wu_off >= 0 && c.KH == 2 && c.stride == 2 && c.pad == 0) {  // runs as a 1x1 conv over the space-to-depth view
+      float* w1 = nullptr;
+      DYF_CUDA_OK(cudaMalloc(&w1, (size_t)c.Cout * 4 * c.Cin * sizeof(float)));
+      int rk = launch_k2s2_to_conv1x1(w_src, w1, c.Cout, c.Cin, s);
+      if (!rk) rk = launch_repack_umma(w1, wq_umma + c.wu_off, c.Cout, 4 * c.Cin, 1, 1, 0, 0, s);
+      if (rk) return rk;
+      DYF_CUDA_OK(cudaStreamSynchronize(s));
+      DYF_CUDA_OK(cudaFree(w1));
+    } else if (c.wu_off >= 0) {
       int rcu = launch_repack_umma(w_src, wq_umma + c.wu_off, c.Cout, c.Cin, c.KH, c.stride, c.pad, c.standardize ? 1 : 0, s);
       if (rcu) return rcu;
     }
@@ -569,6 +579,7 @@ int Net::finalize(cudaStream_t s) {
     DYF_CUDA_OK(cudaMemcpyAsync(d_time_layers, time_layers.data(), time_layers.size() * sizeof(TimeLayer),
                                 cudaMemcpyHostToDevice, s));
   DYF_CUDA_OK(cudaStreamSynchronize(s));
+  clear_tab_cache();  // tables depend on the (re-)loaded parameters
   finalized = true;
   return 0;
 }
@@ -586,7 +597,7 @@ size_t Net::workspace_bytes(int rows) const {
 
 int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
                  const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s, int noise_src, float noise_w,
-                 int src_rows, int group_rows) {
+                 int src_rows, int group_rows, const float* host_times) {
   // `group_rows` consecutive rows share one time value (and hence one set of epilogue tables): `time` then holds
   // rows / group_rows entries (the sampler's logical calls); 1 = one time per row (the public forward)
   if (group_rows < 1 || rows % group_rows) { set_error("internal: bad group_rows"); return DYF_ERR_ARG; }
@@ -594,7 +605,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
   if (!finalized) { set_error("net not finalized (call dyf_net_finalize after loading parameters)"); return DYF_ERR_STATE; }
   if (rows <= 0) { set_error("rows must be positive"); return DYF_ERR_ARG; }
   if (ws_bytes < workspace_bytes(rows)) { set_error("workspace too small"); return DYF_ERR_ARG; }
-  if (d.with_time_emb && !time) { set_error("time is required (with_time_emb=True)"); return DYF_ERR_ARG; }
+  if (d.with_time_emb && !time && !host_times) { set_error("time is required (with_time_emb=True)"); return DYF_ERR_ARG; }
   int ctot = 0;
   for (int i = 0; i < nsrc; ++i) ctot += src_ch[i];
   if (ctot != d.in_channels + d.cond_channels || nsrc > 6) {
@@ -620,20 +631,47 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
     base += align256(bufs[i].row_bytes() * rows);
   }
 
-  // ---- epilogue tables from the time embedding (a5)
+  // ---- epilogue tables from the time embedding (a5).  With a host copy of the times the tables of a time tuple are
+  // computed once and kept (they depend only on the parameters and the times, not on the rows).
   {
-    TimeParams tp{};
-    tp.time = d.with_time_emb ? time : nullptr;
-    tp.packed = packed;
-    if (d.with_time_emb) {
-      tp.w1_off = params[t_w1].off; tp.b1_off = params[t_b1].off;
-      tp.w2_off = params[t_w2].off; tp.b2_off = params[t_b2].off;
+    const size_t tab_bytes = align256((size_t)tab_floats_per_row * tab_rows * sizeof(float));
+    bool compute = true;
+    if (host_times && d.with_time_emb && tab_cache.size() < 4096) {
+      std::vector<float> key(host_times, host_times + tab_rows);
+      auto it = tab_cache.find(key);
+      compute = it == tab_cache.end();
+      if (compute) {
+        float* buf = nullptr;
+        const size_t scratch = align256((size_t)(time_dim + 1) * tab_rows * sizeof(float));
+        DYF_CUDA_OK(cudaMalloc(&buf, 2 * tab_bytes + scratch));
+        it = tab_cache.emplace(key, buf).first;
+      }
+      tabA = it->second;
+      tabB = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(it->second) + tab_bytes);
+      if (compute) {
+        temb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(it->second) + 2 * tab_bytes);
+        float* tdev = temb + (size_t)time_dim * tab_rows;
+        DYF_CUDA_OK(cudaMemcpyAsync(tdev, host_times, (size_t)tab_rows * sizeof(float), cudaMemcpyHostToDevice, s));
+        time = tdev;
+      }
+    } else if (d.with_time_emb && !time) {
+      set_error("time is required (with_time_emb=True)");
+      return DYF_ERR_ARG;
     }
-    tp.dim = d.dim; tp.time_dim = time_dim;
-    tp.layers = d_time_layers; tp.n_layers = (int)time_layers.size();
-    tp.rows = tab_rows; tp.tabA = tabA; tp.tabB = tabB; tp.temb = temb; tp.total_ch = (int)tab_floats_per_row;
-    int rc = launch_time_tables(tp, s);
-    if (rc) return rc;
+    if (compute) {
+      TimeParams tp{};
+      tp.time = d.with_time_emb ? time : nullptr;
+      tp.packed = packed;
+      if (d.with_time_emb) {
+        tp.w1_off = params[t_w1].off; tp.b1_off = params[t_b1].off;
+        tp.w2_off = params[t_w2].off; tp.b2_off = params[t_b2].off;
+      }
+      tp.dim = d.dim; tp.time_dim = time_dim;
+      tp.layers = d_time_layers; tp.n_layers = (int)time_layers.size();
+      tp.rows = tab_rows; tp.tabA = tabA; tp.tabB = tabB; tp.temb = temb; tp.total_ch = (int)tab_floats_per_row;
+      int rc = launch_time_tables(tp, s);
+      if (rc) return rc;
+    }
   }
 
   for (const Op& o : ops) {
@@ -695,8 +733,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.src[0] = bp[o.in0]; p.C[0] = o.c0; p.ld[0] = bufs[o.in0].C;
         p.src[1] = o.in1 >= 0 ? bp[o.in1] : bp[o.in0]; p.C[1] = o.c1; p.ld[1] = o.in1 >= 0 ? bufs[o.in1].C : bufs[o.in0].C;
         p.rows = rows; p.H = bufs[o.in0].H; p.W = bufs[o.in0].W; p.Cout = c.Cout;
-        for (int v = 0; v < 5; ++v) p.w[v] = wq_umma + c.up_off[v];
-        p.wc = w_corner + c.upc_off;
+        for (int v = 0; v < DYF_UP_VARIANTS; ++v) p.w[v] = wq_umma + c.up_off[v];
         p.out = bp[o.out]; p.out_ld = bufs[o.out].C;
         p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;

@@ -89,7 +89,7 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
   float* x_s = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
   float* x0_hat = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
   float* ybuf = reinterpret_cast<float*>(base); base += align256((size_t)kmax * state_n * sizeof(float));
-  float* tbuf = reinterpret_cast<float*>(base); base += align256((size_t)kmax * rows * sizeof(float));
+  base += align256((size_t)kmax * rows * sizeof(float));  // (time vector slot of the workspace layout; times now travel as host values)
   void* net_ws = base;
   const size_t net_ws_bytes = ws_bytes - (size_t)(base - reinterpret_cast<uint8_t*>(ws));
 
@@ -117,10 +117,9 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     if (f_cond_first) push_cond();
     srcs[ns] = x_s; ch[ns++] = C;
     if (!f_cond_first) push_cond();
-    int rc = launch_fill(tbuf, (float)tF[idx], 1, s);
-    if (rc) return rc;
+    const float th = (float)tF[idx];  // host copy of the time: the net keeps the epilogue tables of times it has seen
     dyf_dropout dr{0, seed, call++};
-    return F->forward(rows, srcs, ch, ns, tbuf, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows);
+    return F->forward(rows, srcs, ch, ns, nullptr, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows, &th);
   };
   // k logical interpolator calls at times t[0..k) sharing the inputs (ic, x0_hat); outputs land in ybuf[j]
   auto run_I = [&](const double* t, int k) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
@@ -131,13 +130,10 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     srcs[ns] = ic; ch[ns++] = d.window_channels;
     srcs[ns] = x0_hat; ch[ns++] = C;
     if (!i_cond_first && stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
-    for (int j = 0; j < k; ++j) {
-      int rc = launch_fill(tbuf + j, (float)t[j], 1, s);
-      if (rc) return rc;
-    }
+    std::vector<float> th(t, t + k);  // host copy of the times: the net keeps the epilogue tables of tuples it has seen
     dyf_dropout dr{d.enable_interpolator_dropout ? 1 : 0, seed, call};
     call += k;
-    return I->forward(k * rows, srcs, ch, ns, tbuf, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows);
+    return I->forward(k * rows, srcs, ch, ns, nullptr, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows, th.data());
   };
 
   for (int i = 0; i < n; ++i) {
