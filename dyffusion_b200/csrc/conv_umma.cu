@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
   const int tiles_per_row = tiles_x * tiles_y;
   // whole filter fits the weight ring and every work item uses the same n-tile: load it once, never release it
   const bool b_resident = n_tiles == 1 && nchunks * (G::TAPS / GT) == BS;
+  // Work items go round-robin over the CTAs in runs of `cw` consecutive items.  Multi-chunk layers use cw = 1 (concurrent
+  // CTAs on neighbouring tiles: halos hit in L2, accesses spread over the DRAM partitions; contiguous per-CTA slices were
+  // measured 10-50 % slower); short single-chunk layers (stem, readout, 1x1) are bound by per-item latencies, and runs of 8
+  // tiles of one image let them keep their epilogue tables.
+  const int cw = (nchunks * G::TAPS <= 9 && num_work >= 16 * (int)gridDim.x) ? 8 : 1;  // (only with plenty of items per CTA)
 
   if (tid == 0) {
     for (int i = 0; i < AS; ++i) { mbar_init(smem_u32(&bars->a_full[i]), TMA ? 1 : PROD_THREADS); mbar_init(smem_u32(&bars->a_empty[i]), 1); }
@@ -169,24 +174,32 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     const float slope = act == ACT_NONE ? 1.f : act == ACT_RELU ? 0.f : 0.2f;
     const uint32_t thresh = p.drop.thresh;
     const float dscale = p.drop.scale;
-    int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    int it = 0, tab_key = -1, tab_buf = 0;
+    for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
+    for (int w = w0; w < min(w0 + cw, num_work); ++w, ++it) {
       int n_tile, row, oy0, ox0;
       decode(w, n_tile, row, oy0, ox0);
       const int acc = it & 1;
       const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
       const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
       const int oy = oy0 + (m_local >> 3);
-      // stage this item's epilogue tables in shared memory (one global round trip per item instead of one per 8 columns)
-      float* const tA = sTab + acc * 2 * BN;
-      float* const tB = tA + BN;
-      if (tid < BN) {
-        const int col = n_tile * BN + tid;
-        const size_t off = (size_t)(row / p.tab_div) * p.Cout + col;
-        tA[tid] = col < p.Cout ? __ldg(p.tabA + off) : 0.f;
-        tB[tid] = col < p.Cout ? __ldg(p.tabB + off) : 0.f;
+      // epilogue tables of (table row, n-tile) staged in shared memory; re-staged only when the key changes (contiguous
+      // work ranges: once per image), into the other buffer so that one barrier per change suffices
+      const int tkey = (row / p.tab_div) * n_tiles + n_tile;
+      if (tkey != tab_key) {
+        tab_key = tkey;
+        tab_buf ^= 1;
+        float* const dst = sTab + tab_buf * 2 * BN;
+        if (tid < BN) {
+          const int col = n_tile * BN + tid;
+          const size_t off = (size_t)(row / p.tab_div) * p.Cout + col;
+          dst[tid] = col < p.Cout ? __ldg(p.tabA + off) : 0.f;
+          dst[BN + tid] = col < p.Cout ? __ldg(p.tabB + off) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const float* const tA = sTab + tab_buf * 2 * BN;
+      const float* const tB = tA + BN;
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
       constexpr int COLS = BN / (EPI_WARPS / 4);  // columns drained by this warp
@@ -260,7 +273,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     if constexpr (TMA) {
       if (ptid == 0) {
         int ca = 0;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
+      for (int w = w0; w < min(w0 + cw, num_work); ++w) {
           int n_tile, row, oy0, ox0;
           decode(w, n_tile, row, oy0, ox0);
           for (int c = 0; c < nchunks; ++c, ++ca) {
@@ -284,7 +298,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     const int g8 = ptid % G::CPL;                           // fixed 8-channel group of this thread
     const __nv_bfloat16* const in_base = p.in;
     int ca = 0;                                             // running chunk counter (A ring position)
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
+      for (int w = w0; w < min(w0 + cw, num_work); ++w) {
       int n_tile, row, oy0, ox0;
       decode(w, n_tile, row, oy0, ox0);
       int src_off[ITERS];                                   // element offset of the patch pixel, -1 = outside the image
@@ -342,7 +357,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       constexpr int AK = (TMA ? 32 : 2 * PLANE) >> 4;  // descriptor step between the K = 16 slices of a chunk
       constexpr int BK = (2 * BN * 16) >> 4;
       int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;  // ring positions / phase parities
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
+    for (int w = w0; w < min(w0 + cw, num_work); ++w, ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -382,7 +398,10 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     if (lane == 0) {
       const int per_tile = nchunks * (G::TAPS / GT);
       int sb = 0, pb = 1;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      bool loaded = false;  // resident filter: loaded by the first work item only
+      for (int w0 = blockIdx.x * cw; w0 < num_work && !(b_resident && loaded); w0 += gridDim.x * cw)
+      for (int w = w0; w < min(w0 + cw, num_work) && !(b_resident && loaded); ++w) {
+        loaded = true;
         const int n_tile = w % n_tiles;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wblob) + (size_t)n_tile * per_tile * B_STAGE;
         for (int i = 0; i < per_tile; ++i) {
@@ -391,7 +410,6 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
           bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
           if (++sb == BS) { sb = 0; pb ^= 1; }
         }
-        if (b_resident) break;
       }
     }
   }

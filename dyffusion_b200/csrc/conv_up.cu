@@ -165,7 +165,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
 
   if (warp < EPI_WARPS) {
     // =============================== epilogue: TMEM -> affine/activation/dropout -> depth-to-space stores ==========
-    int it = 0;
+    int it = 0, tab_key = -1, tab_buf = 0;
     const int quarter = warp & 3, m_local = quarter * 32 + lane;
     constexpr int COLS = BN / (EPI_WARPS / 4);
     const int cbeg = (warp >> 2) * COLS;
@@ -173,15 +173,21 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
       int n_tile, img, i0, j0, side;
       decode(w, n_tile, img, i0, j0, side);
       const int acc = it & 1;
-      float* const sA_tab = sTab + acc * 2 * BN;
-      if constexpr (KIND == K_MAIN) {  // one image per item: stage its epilogue tables once in shared memory
-        if (tid < BN) {
-          const size_t off = (size_t)(img / p.tab_div) * p.Cout + (n_tile * BN + tid) % p.Cout;
-          sA_tab[tid] = __ldg(p.tabA + off);
-          sA_tab[BN + tid] = __ldg(p.tabB + off);
+      if constexpr (KIND == K_MAIN) {  // one image per item: its epilogue tables are staged in shared memory, re-staged
+        const int tkey = (img / p.tab_div) * n_tiles + n_tile;  // (into the other buffer) only when (table row, n-tile) changes
+        if (tkey != tab_key) {
+          tab_key = tkey;
+          tab_buf ^= 1;
+          float* const dst = sTab + tab_buf * 2 * BN;
+          if (tid < BN) {
+            const size_t off = (size_t)(img / p.tab_div) * p.Cout + (n_tile * BN + tid) % p.Cout;
+            dst[tid] = __ldg(p.tabA + off);
+            dst[BN + tid] = __ldg(p.tabB + off);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
+      const float* const sA_tab = sTab + tab_buf * 2 * BN;
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -338,8 +344,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
     const uint32_t tmem_base = bars->tmem_base;
     const CUtensorMap* m0 = &maps.m[phase][0];
     const CUtensorMap* m1 = &maps.m[phase][1];
-    // the work items of all phases form one round-robin sequence over the CTAs: a phase starts at the CTA after the one
-    // that took the previous phase's last item, so CTAs with one MAIN tile less pick up the border tiles first
+    // The work items of all phases form one round-robin sequence over the CTAs (concurrent CTAs work on neighbouring
+    // tiles: shared halos hit in L2 and the accesses spread over the DRAM partitions -- contiguous per-CTA slices were
+    // measured 50 % slower); a phase starts at the CTA after the one that took the previous phase's last item, so CTAs with
+    // one MAIN tile less pick up the border tiles first.
     const int first = (int)((blockIdx.x + gridDim.x - done % gridDim.x) % gridDim.x);
     if (phase == K_MAIN) up_phase<K_MAIN>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);
     else if (phase == K_ROW) up_phase<K_ROW>(p, smem, tmem_base, wk.tiles_a[phase], n_tiles, wk.num_work[phase], first, m0, m1);

@@ -101,3 +101,16 @@ def test_fused_block_draws_the_same_dropout_masks():
         y_nodrop = m0(x, time=t, condition=c).cpu()
     assert H.rel_l2(outs[0], outs[1]) <= 2 * TOL, H.rel_l2(outs[0], outs[1])
     assert H.rel_l2(outs[0], y_nodrop) > 5 * TOL  # dropout was really on
+
+
+def test_many_rows_multiple_work_rounds_per_cta():
+    """Enough rows that every persistent CTA walks several rounds of its work list in every kernel (single-chunk layers with
+    a resident filter included): must terminate, stay finite, and equal the same rows run as a small batch, bit for bit."""
+    x, c, t = _inputs(20)
+    with torch.no_grad():
+        m, _ = _build((256, 256), True)
+        y = m(x, time=t, condition=c)
+        y_tail = m(x[17:20], time=t[17:20], condition=c[17:20])
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert torch.equal(y[17:20], y_tail)
