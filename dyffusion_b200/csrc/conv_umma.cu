@@ -112,7 +112,9 @@ template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
 __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap,
-                                                              const __grid_constant__ CUtensorMap tmap2, int nch_split) {
+                                                              const __grid_constant__ CUtensorMap tmap2,
+                                                              const __grid_constant__ CUtensorMap tmap3,
+                                                              const __grid_constant__ CUtensorMap tmap4, int nch_split) {
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
   constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
@@ -121,7 +123,15 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
   static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
   constexpr int PWT = TILE_W * T + G::HALO;  // patch width of the super-tile (TMA mode)
   constexpr int PIXT = G::PH * PWT;
-  constexpr int A_STAGE = TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
+  // Stride-2 TMA mode: the patch is four boxes, one per (row parity, column parity) VIEW of the input (tensor maps with
+  // pixel pitch 2 and row pitch 2: quarter-resolution images; zero fill outside = the conv's padding).  Inside a view
+  // the stride-2 walk of a tap is a unit-stride one, so every tap is a start-address shift in one of the four regions:
+  // tap (ky, kx) reads view ((ky+1)&1, (kx+1)&1) at box offset (ky>>1, kx>>1).  32-channel chunks = 64-byte pixel rows
+  // with the 64-byte swizzle.
+  constexpr bool S2TMA = TMA && MODE == S2K4;
+  constexpr int VW = TILE_W * T + 1, VH = TILE_H + 1;                      // view box: 17 rows x (8T+1) pixels
+  constexpr int VREGION = ((VH * VW * 64 + 1023) / 1024) * 1024;
+  constexpr int A_STAGE = S2TMA ? 4 * VREGION : TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
   constexpr int B_TAP = BN * G::CH * 2;    // one tap of one chunk: [k8][BN rows][16 B]
   constexpr int B_STAGE = GT * B_TAP;      // a weight stage carries GT taps
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -281,6 +291,18 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
             const int st = ca % AS;
             mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
             const uint32_t bar = smem_u32(&bars->a_full[st]);
+            if constexpr (S2TMA) {
+              mbar_expect_tx(bar, 4 * VH * VW * 64);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {  // v = row parity * 2 + column parity; odd views start one view pixel earlier
+                const uint64_t tmv = reinterpret_cast<uint64_t>(v == 0 ? &tmap : v == 1 ? &tmap2 : v == 2 ? &tmap3 : &tmap4);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                    ::"r"(smem_u32(sA + st * A_STAGE + v * VREGION)), "l"(tmv), "r"(c * G::CH), "r"(ox0 - (v & 1)),
+                      "r"(oy0 - (v >> 1)), "r"(row), "r"(bar) : "memory");
+              }
+              continue;
+            }
             mbar_expect_tx(bar, PIXT * 128);
             // nch_split > 0: the K axis is the concatenation of two tensor views (chunks [0, nch_split) / the rest)
             const bool second = nch_split > 0 && c >= nch_split;
@@ -347,8 +369,9 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
-      const uint32_t a_hi = TMA ? ((uint32_t)(((PWT * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
-                                : ((uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14));
+      const uint32_t a_hi = S2TMA ? ((uint32_t)(((VW * 64) >> 4) & 0x3FFF) | (1u << 14) | (4u << 29))  // SWIZZLE_64B
+                            : TMA ? ((uint32_t)(((PWT * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
+                                  : ((uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14));
       const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
       const uint32_t a_lo0 = ((uint32_t)(TMA ? 1 : (PLANE >> 4)) << 16) | (smem_u32(sA) >> 4);  // LBO | start address
       const uint32_t b_lo0 = ((uint32_t)((BN * 16) >> 4) << 16) | (smem_u32(sB) >> 4);
@@ -377,8 +400,9 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
 #pragma unroll
             for (int t = 0; t < GT; ++t) {
               const int tap = g * GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
-              const int a_off = TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
-              constexpr int TILE_STEP = TILE_W * (TMA ? 128 : 16);  // 8 pixels further along the patch row
+              const int a_off = S2TMA ? ((((ky + 1) & 1) * 2 + ((kx + 1) & 1)) * VREGION + ((ky >> 1) * VW + (kx >> 1)) * 64)
+                                : TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
+              constexpr int TILE_STEP = TILE_W * (S2TMA ? 64 : TMA ? 128 : 16);  // 8 pixels further along the patch row
 #pragma unroll
               for (int tile = 0; tile < T; ++tile)
                 umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_STEP) >> 4),
@@ -468,6 +492,8 @@ template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1,
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
+template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };    // 152 KB views +  64 KB weights
+template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   // 152 KB views +  64 KB weights
 template <> struct Stages<S2K4, 128, false, 2> { static constexpr int T = 1, GT = 1, A = 2, B = 17; };  //  77 KB patches + 136 KB weights
 template <> struct Stages<S2K4, 128, false, 3> { static constexpr int T = 1, GT = 1, A = 4, B = 8; };   // 154 KB patches +  64 KB weights
 
@@ -492,7 +518,8 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   using St = Stages<MODE, BN, TMA, V>;
   constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
   using G = Geo<MODE, TMA ? 1 : T>;
-  constexpr int a_stage = TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE, T>::A_STAGE;
+  constexpr int a_stage = (TMA && MODE == S2K4) ? 4 * ((((TILE_H + 1) * (TILE_W * T + 1) * 64 + 1023) / 1024) * 1024)
+                          : TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE, T>::A_STAGE;
   constexpr int smem = AS * a_stage + BS * GT * BN * G::CH * 2 + (((int)sizeof(Barriers<AS, BS>) + 15) & ~15) + 4 * BN * 4 + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(2 * T * BN <= 512, "TMEM budget exceeded");
@@ -503,8 +530,8 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     DYF_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  CUtensorMap tmap{}, tmap2{};
-  if (views) { tmap = views[0]; tmap2 = views[1]; }
+  CUtensorMap tmap{}, tmap2{}, tmap3{}, tmap4{};
+  if (views) { tmap = views[0]; tmap2 = views[1]; if (MODE == S2K4) { tmap3 = views[2]; tmap4 = views[3]; } }
   else if (TMA && make_patch_tmap(p, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
   const int tiles_x = (p.Wo + TILE_W * T - 1) / (TILE_W * T), tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
   const int n_tiles = (p.Cout + BN - 1) / BN;
@@ -515,7 +542,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
   conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
-                                                                                (int)work, tmap, tmap2, nch_split);
+                                                                                (int)work, tmap, tmap2, tmap3, tmap4, nch_split);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -606,6 +633,28 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
       if (rc != 0) return rc;
     }
     return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
+  }
+  if (want_tma && !((p.Hi | p.Wi) & 1)) {  // four parity views of the input, 64-byte swizzle
+    constexpr int T2 = Stages<S2K4, 128, true>::T;
+    using Key = std::tuple<const void*, int, int, int, int>;
+    struct Quad { CUtensorMap m[4]; };
+    static std::map<Key, Quad> cache;
+    const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin};
+    auto it = cache.find(key);
+    bool ok = true;
+    if (it == cache.end()) {
+      Quad q;
+      const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi / 2, (cuuint64_t)p.Hi / 2, (cuuint64_t)p.rows};
+      const cuuint64_t strides[3] = {(cuuint64_t)4 * p.Cin, (cuuint64_t)4 * p.Wi * p.Cin, (cuuint64_t)2 * p.Hi * p.Wi * p.Cin};
+      const cuuint32_t box[4] = {32, TILE_W * T2 + 1, TILE_H + 1, 1};
+      for (int v = 0; v < 4 && ok; ++v)
+        ok = make_tmap4(p.in + ((size_t)(v >> 1) * p.Wi + (v & 1)) * p.Cin, dims, strides, box, &q.m[v], CU_TENSOR_MAP_SWIZZLE_64B) == 0;
+      if (ok) {
+        if (cache.size() > 1024) cache.clear();
+        it = cache.emplace(key, q).first;
+      }
+    }
+    if (ok) return n64 ? launch_t<64, S2K4, true>(p, stream, it->second.m) : launch_t<128, S2K4, true>(p, stream, it->second.m);
   }
   static const char* env_c = getenv("DYF_S2K4_CFG");
   if (!n64 && env_c && env_c[0] == '2') return launch_t<128, S2K4, false, 2>(p, stream);
