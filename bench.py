@@ -221,10 +221,16 @@ def run_engine(args):
         units_per_step = world * rows * H * W * n_steps_sched
         value = units_per_step * args.steps / (ms_total / 1e3)
         e2e = units_per_step * args.steps / float(e2e_s.item())
-        conv = {k: prof[k] for k in ("conv_mma", "conv_umma")}
-        dom = max(conv, key=lambda k: conv[k]["ms"])
+        conv = {k: prof[k] for k in ("conv_mma", "conv_umma", "conv_up")}
+        dom = max(conv, key=lambda k: conv[k]["ms"])  # dominant kernel class of the step (by device time)
         d = conv[dom]
         ach = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+        # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json): bytes per
+        # launch averaged over the launches of one 64-row forward, next to the algorithmic bytes of the same launches
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         total_kernel_ms = sum(v["ms"] for v in prof.values())
         flop_step = rows * (16 * GF_FORECASTER + 44 * GF_INTERPOLATOR) * 1e9
         line = {
@@ -240,7 +246,9 @@ def run_engine(args):
                     "d2h_bytes_per_step": int(host_out.numel() * 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                         "frac": ach / pk["tflops"], "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_detail": traffic, "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launches"]),
+                         "peak_source": pk["source"],
                          "launches": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
                          "share_of_kernel_time": d["ms"] / total_kernel_ms if total_kernel_ms else None,
                          "whole_step_tflops": flop_step * args.steps / (ms_total / 1e3) / 1e12},

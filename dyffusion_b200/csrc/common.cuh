@@ -16,7 +16,7 @@ void count_launch(int n = 1);
 // Optional per-launch CUDA-event bracketing (bench.py's roofline measurement): when enabled, every kernel launch
 // is timed on its own stream and accumulated per kernel class.
 enum KernelClass : int { KC_CONV_MMA = 0, KC_CONV_UMMA, KC_PACK, KC_UPSAMPLE, KC_GROUPNORM, KC_READOUT, KC_TIME,
-                         KC_ELEMENTWISE, KC_ATTENTION, KC_COUNT };
+                         KC_ELEMENTWISE, KC_ATTENTION, KC_CONV_UP, KC_COUNT };
 struct ProfScope {
   cudaStream_t s;
   int idx;

@@ -490,7 +490,7 @@ int launch_conv_up(const UpConvParams& p, cudaStream_t stream) {
   const int Cin = p.C[0] + p.C[1];
   const double flops = 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin;  // = the reference conv on the upsampled grid
   const double bytes = 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin);
-  ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
+  ProfScope prof(stream, KC_CONV_UP, flops, bytes);
   conv_up_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p, wk, n_tiles, maps);
   DYF_LAUNCH_OK("conv_up_kernel");
   return 0;

@@ -93,7 +93,7 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
             "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_read"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
-                  "attention"]
+                  "attention", "conv_up"]
 
 
 class EngineError(RuntimeError):
