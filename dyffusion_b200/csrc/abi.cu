@@ -15,6 +15,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 // ---- launch profiler
 struct ProfRec { cudaEvent_t a, b; int klass; double flops, bytes; };
 static bool g_prof_on = false;
+static int g_prof_only = -1;  // -1 = every kernel class, else only launches of this class are bracketed by events
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static cudaEvent_t take_event() {
@@ -24,7 +25,7 @@ static cudaEvent_t take_event() {
   return e;
 }
 ProfScope::ProfScope(cudaStream_t stream, int klass, double flops, double bytes) : s(stream), idx(-1) {
-  if (!g_prof_on) return;
+  if (!g_prof_on || (g_prof_only >= 0 && klass != g_prof_only)) return;
   ProfRec r{take_event(), take_event(), klass, flops, bytes};
   cudaEventRecord(r.a, s);
   idx = (int)g_prof.size();
@@ -52,6 +53,12 @@ extern "C" {
 int dyf_abi_version(void) { return DYF_ABI_VERSION; }
 const char* dyf_last_error(void) { return get_error(); }
 uint64_t dyf_launch_count(void) { return g_launches.load(); }
+
+int dyf_profile_filter(int32_t klass) {
+  if (klass >= KC_COUNT) { set_error("bad kernel class"); return DYF_ERR_ARG; }
+  g_prof_only = klass < 0 ? -1 : klass;
+  return 0;
+}
 
 int dyf_profile_enable(int32_t on) {
   if (!on) {

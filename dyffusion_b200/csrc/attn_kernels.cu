@@ -56,76 +56,139 @@ __global__ void __launch_bounds__(256) channel_ln_kernel(const ChannelLNParams p
 // ---------------------------------------------------------------------------------------------- linear attention
 // qkv: [rows, n, 3*heads*DH] with q | k | v blocks, heads-major inside each block ("b (h c) x y -> b h c (x y)").
 // Pass 1 (one block per (head, row)): ctx[d][e] = sum_n softmax_n(k)[d, n] * v[e, n] / n.
+// Phase A: max over n of k[d, n].  Phase B: every warp walks its own chunks of 16 positions: stage exp(k - max) and v as
+// fp32 in a private shared-memory tile (128-bit loads, 8 channels per lane), then accumulate a 4 (d) x 8 (e) register
+// tile per lane from broadcast float4 reads (3 LDS per 32 FMA).  Phase C: the 8 per-warp partial sums are combined in
+// warp order (fixed order => bit-reproducible).
+constexpr int CTX_POS = 16;  // positions per warp chunk
 __global__ void __launch_bounds__(256) linattn_ctx_kernel(const AttnParams p) {
+  __shared__ __align__(16) float s_tile[8][2][CTX_POS][DH];  // per warp: exp(k - max) | v ; reused for the final combine
   __shared__ float s_red[8][DH];
-  __shared__ float s_max[DH], s_sum[DH];
-  __shared__ float s_k[32][DH + 1], s_v[32][DH + 1];
+  __shared__ float s_max[DH], s_den[8][DH];
   const int h = blockIdx.x, r = blockIdx.y;
   const int ld = 3 * p.heads * DH;
   const __nv_bfloat16* kbase = p.qkv + (size_t)r * p.n * ld + p.heads * DH + h * DH;
   const __nv_bfloat16* vbase = kbase + p.heads * DH;
-  const int d = threadIdx.x & 31, g = threadIdx.x >> 5;  // 8 groups of 32 threads
-  // max over n of k[d, n]
-  float mx = -INFINITY;
-  for (int n = g; n < p.n; n += 8) mx = fmaxf(mx, __bfloat162float(kbase[(size_t)n * ld + d]));
-  s_red[g][d] = mx;
-  __syncthreads();
-  if (g == 0) {
-    float m = s_red[0][d];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i][d]);
-    s_max[d] = m;
-  }
-  __syncthreads();
-  const float kmax = s_max[d];
-  // thread (d, g) accumulates ctx[d][4g .. 4g+3] and (g == 0) the softmax denominator of row d
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, den = 0.f;
-  for (int n0 = 0; n0 < p.n; n0 += 32) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {  // ---- phase A
+    float mx = -INFINITY;
+    for (int n = warp; n < p.n; n += 8) mx = fmaxf(mx, __bfloat162float(kbase[(size_t)n * ld + lane]));
+    s_red[warp][lane] = mx;
     __syncthreads();
-    for (int i = g; i < 32; i += 8) {  // stage 32 positions: exp(k - max) and v
-      const int n = n0 + i;
-      const bool ok = n < p.n;
-      s_k[i][d] = ok ? __expf(__bfloat162float(kbase[(size_t)n * ld + d]) - s_max[d]) : 0.f;
-      s_v[i][d] = ok ? __bfloat162float(vbase[(size_t)n * ld + d]) : 0.f;
+    if (warp == 0) {
+      float m = s_red[0][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i][lane]);
+      s_max[lane] = m;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const float ek = s_k[i][d];
-      den += ek;
+  }
+  // ---- phase B
+  const int sp = lane >> 2, sc = (lane & 3) * 8;  // staging: this lane loads channels [sc, sc+8) of positions sp, sp+8
+  float kmax[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = fmaf(ek, s_v[i][4 * g + e], acc[e]);
+  for (int j = 0; j < 8; ++j) kmax[j] = s_max[sc + j];
+  const int dg = (lane >> 2) * 4, eg = (lane & 3) * 8;  // accumulation tile: d in [dg, dg+4), e in [eg, eg+8)
+  float acc[4][8], den[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+  float (*tk)[DH] = s_tile[warp][0];
+  float (*tv)[DH] = s_tile[warp][1];
+  for (int n0 = warp * CTX_POS; n0 < p.n; n0 += 8 * CTX_POS) {
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int i = sp + 8 * half, n = n0 + i;
+      float fk[8], fv[8];
+      if (n < p.n) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(kbase + (size_t)n * ld + sc)), fk);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(vbase + (size_t)n * ld + sc)), fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fk[j] = __expf(fk[j] - kmax[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { fk[j] = 0.f; fv[j] = 0.f; }
+      }
+      *reinterpret_cast<float4*>(&tk[i][sc]) = make_float4(fk[0], fk[1], fk[2], fk[3]);
+      *reinterpret_cast<float4*>(&tk[i][sc + 4]) = make_float4(fk[4], fk[5], fk[6], fk[7]);
+      *reinterpret_cast<float4*>(&tv[i][sc]) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+      *reinterpret_cast<float4*>(&tv[i][sc + 4]) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int i = 0; i < CTX_POS; ++i) {
+      const float4 kd = *reinterpret_cast<const float4*>(&tk[i][dg]);
+      const float4 v0 = *reinterpret_cast<const float4*>(&tv[i][eg]), v1 = *reinterpret_cast<const float4*>(&tv[i][eg + 4]);
+      const float ka[4] = {kd.x, kd.y, kd.z, kd.w}, va[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        den[a] += ka[a];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(ka[a], va[e], acc[a][e]);
+      }
     }
   }
-  (void)kmax;
-  if (g == 0) s_sum[d] = den;
-  __syncthreads();
-  const float inv = 1.f / (s_sum[d] * (float)p.n);  // softmax normalisation and the v / (h*w) rescale (attention.py:42)
-  float* ctx = p.ctx + (((size_t)r * p.heads + h) * DH + d) * DH + 4 * g;
+  // ---- phase C: per-warp partials -> shared memory (the warp's own tile: 2 * 16 * 32 floats = one 32 x 32 matrix)
+  __syncwarp();
+  float* part = &s_tile[warp][0][0][0];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) ctx[e] = acc[e] * inv;
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[(dg + a) * DH + eg + e] = acc[a][e];
+    if ((lane & 3) == 0) s_den[warp][dg + a] = den[a];
+  }
+  __syncthreads();
+  float* ctx = p.ctx + ((size_t)r * p.heads + h) * DH * DH;
+  for (int idx = threadIdx.x; idx < DH * DH; idx += blockDim.x) {
+    const int d = idx / DH;
+    float sum = 0.f, dsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sum += (&s_tile[w][0][0][0])[idx]; dsum += s_den[w][d]; }
+    ctx[idx] = sum / (dsum * (float)p.n);  // softmax normalisation and the v / (h*w) rescale (attention.py:42)
+  }
 }
 
-// Pass 2: out[e, n] = sum_d ctx[d][e] * softmax_d(q)[d, n] * DH^-0.5 ; one warp per position, lane = d then e.
+// Pass 2: out[e, n] = sum_d ctx[d][e] * softmax_d(q)[d, n] * DH^-0.5.  One THREAD per position: its 32 q values (64
+// contiguous bytes) are soft-maxed in registers, the 32 x 32 context matrix is read from shared memory as broadcast
+// float4 rows, and the 32 outputs leave as four 128-bit stores -- no cross-lane traffic at all.
 __global__ void __launch_bounds__(256) linattn_out_kernel(const AttnParams p) {
-  __shared__ float s_ctx[DH][DH + 1];
+  __shared__ __align__(16) float s_ctx[DH][DH];
   const int h = blockIdx.y, r = blockIdx.z;
   const float* ctx = p.ctx + ((size_t)r * p.heads + h) * DH * DH;
   for (int i = threadIdx.x; i < DH * DH; i += blockDim.x) s_ctx[i / DH][i % DH] = ctx[i];
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.n) return;
   const int ld = 3 * p.heads * DH;
-  const float scale = rsqrtf((float)DH);
-  for (int n = blockIdx.x * 8 + warp; n < p.n; n += gridDim.x * 8) {
-    const float q = __bfloat162float(p.qkv[((size_t)r * p.n + n) * ld + h * DH + lane]);
-    const float m = warp_max(q);
-    const float e = __expf(q - m);
-    const float qs = e / warp_sum(e) * scale;
-    float o = 0.f;
+  const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + ((size_t)r * p.n + n) * ld + h * DH);
+  float q[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o = fmaf(s_ctx[d][lane], __shfl_sync(0xffffffffu, qs, d), o);
-    p.out[((size_t)r * p.n + n) * (p.heads * DH) + h * DH + lane] = __float2bfloat16_rn(o);
+  for (int i = 0; i < 4; ++i) unpack8(__ldg(qp + i), q + 8 * i);
+  float m = q[0];
+#pragma unroll
+  for (int d = 1; d < DH; ++d) m = fmaxf(m, q[d]);
+  float sum = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) { q[d] = __expf(q[d] - m); sum += q[d]; }
+  const float norm = rsqrtf((float)DH) / sum;
+  float o[DH];
+#pragma unroll
+  for (int e = 0; e < DH; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {
+    const float qs = q[d] * norm;
+#pragma unroll
+    for (int e4 = 0; e4 < DH / 4; ++e4) {
+      const float4 c = *reinterpret_cast<const float4*>(&s_ctx[d][4 * e4]);
+      o[4 * e4 + 0] = fmaf(c.x, qs, o[4 * e4 + 0]); o[4 * e4 + 1] = fmaf(c.y, qs, o[4 * e4 + 1]);
+      o[4 * e4 + 2] = fmaf(c.z, qs, o[4 * e4 + 2]); o[4 * e4 + 3] = fmaf(c.w, qs, o[4 * e4 + 3]);
+    }
   }
+  uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)r * p.n + n) * (p.heads * DH) + h * DH);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) op[i] = pack8(o + 8 * i);
 }
 
 // ---------------------------------------------------------------------------------------------- full attention
@@ -202,8 +265,7 @@ int launch_linear_attention(const AttnParams& p, cudaStream_t s) {
   ProfScope prof(s, KC_ATTENTION, 4.0 * p.rows * p.heads * (double)p.n * DH * DH);
   linattn_ctx_kernel<<<dim3(p.heads, p.rows), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("linattn_ctx_kernel");
-  const int gx = cdiv(p.n, 8 * 8);
-  linattn_out_kernel<<<dim3(gx, p.heads, p.rows), 256, 0, s>>>(p);
+  linattn_out_kernel<<<dim3(cdiv(p.n, 256), p.heads, p.rows), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("linattn_out_kernel");
   return 0;
 }

@@ -57,7 +57,8 @@ struct GroupNormParams {
   const float* tabA;        // [rows, C] (scale + 1) or nullptr
   const float* tabB;        // [rows, C] shift or nullptr
   const __nv_bfloat16* res; // optional residual [rows, HW, res_ld], added last
-  float* stats;             // [rows, G, 32 slabs, 2] scratch: per-slab partial sums, combined in fixed order
+  float* stats;             // scratch, gn_scratch_floats(C, G) per row: [rows, G, 32 slabs, 2] per-slab partial sums
+                            // (combined in fixed order) followed by the folded per-(row, channel) [rows, 2, C] (A, B)
   int slabs;                // set by the launcher
   int rows, HW, C, G, res_ld;
   int tab_div;              // table row = r / tab_div
@@ -66,6 +67,7 @@ struct GroupNormParams {
   DropCfg drop;
 };
 int launch_groupnorm(const GroupNormParams& p, cudaStream_t s);
+int gn_scratch_floats(int C, int G);  // floats of `stats` scratch per row
 
 // ---- Navier-Stokes readout: ConvTranspose2d(64->Cout, k4, s2, p1) on the Hs x Ws map followed by the bilinear
 //      resize (2Hs x 2Ws) -> (Ho x Wo); only the pixels the resize samples are ever computed.  fp32 NCHW output.

@@ -319,8 +319,34 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormPar
   }
 }
 
-// pass 2: normalise + affine + time scale/shift + activation + dropout + residual
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormParams p) {
+// pass 2 (tiny): per (row, channel) fold statistics, affine and the time scale/shift into y = x * A + B:
+//   A = rstd * gamma * (scale + 1),  B = (beta - mean * rstd * gamma) * (scale + 1) + shift
+// (slab partials are combined in a fixed order).  ab: [rows][2][C] behind the slab partials.
+__global__ void __launch_bounds__(256) groupnorm_fold_kernel(const GroupNormParams p, float* __restrict__ ab) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int cpg = p.C / p.G, g = c / cpg;
+    const float n = (float)p.HW * (float)cpg;
+    float sum1 = 0.f, sum2 = 0.f;
+    const float* st = p.stats + ((size_t)r * p.G + g) * GN_SLABS * 2;
+    for (int sl = 0; sl < p.slabs; ++sl) { sum1 += st[2 * sl]; sum2 += st[2 * sl + 1]; }  // fixed order
+    const float mean = sum1 / n;
+    const float var = fmaxf(sum2 / n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    float A = rstd * __ldg(p.gamma + c);
+    float B = __ldg(p.beta + c) - mean * A;
+    if (p.tabA) {
+      const float tA = __ldg(p.tabA + (size_t)(r / p.tab_div) * p.C + c), tB = __ldg(p.tabB + (size_t)(r / p.tab_div) * p.C + c);
+      A *= tA;
+      B = B * tA + tB;
+    }
+    ab[((size_t)r * 2 + 0) * p.C + c] = A;
+    ab[((size_t)r * 2 + 1) * p.C + c] = B;
+  }
+}
+
+// pass 3: y = act(x * A + B) -> dropout -> + residual
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormParams p, const float* __restrict__ ab) {
   const int chunks = p.C >> 3;
   const long long total = (long long)p.rows * p.HW * chunks;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -329,23 +355,14 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormPar
   const long long m = idx / chunks;
   const int r = (int)(m / p.HW);
   const int c0 = ch << 3;
-  const int cpg = p.C / p.G;
-  const int g = c0 / cpg;
-  const float n = (float)p.HW * (float)cpg;
-  float sum1 = 0.f, sum2 = 0.f;
-  const float* st = p.stats + ((size_t)r * p.G + g) * GN_SLABS * 2;
-  for (int sl = 0; sl < p.slabs; ++sl) { sum1 += st[2 * sl]; sum2 += st[2 * sl + 1]; }  // fixed order
-  const float mean = sum1 / n;
-  const float var = fmaxf(sum2 / n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + p.eps);
+  const float4* A = reinterpret_cast<const float4*>(ab + ((size_t)r * 2 + 0) * p.C + c0);
+  const float4* B = reinterpret_cast<const float4*>(ab + ((size_t)r * 2 + 1) * p.C + c0);
+  const float4 a0 = __ldg(A), a1 = __ldg(A + 1), b0 = __ldg(B), b1 = __ldg(B + 1);
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float f[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.C + c0)), f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float v = (f[j] - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
-    if (p.tabA) v = v * __ldg(p.tabA + (size_t)(r / p.tab_div) * p.C + c0 + j) + __ldg(p.tabB + (size_t)(r / p.tab_div) * p.C + c0 + j);
-    f[j] = apply_act(v, p.act);
-  }
+  for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], av[j], bv[j]), p.act);
   if (p.drop.thresh) {
     const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.C + c0);
 #pragma unroll
@@ -727,6 +744,8 @@ int launch_upsample(const UpsampleParams& p, cudaStream_t s) {
   return 0;
 }
 
+int gn_scratch_floats(int C, int G) { return 2 * G * GN_SLABS + 2 * C; }  // per row: slab partials + folded (A, B)
+
 int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
   const int chunks = p.C >> 3;
   if (p.C % (8 * p.G) != 0 || chunks > 256 || 256 % chunks != 0 || p.G > 64) {
@@ -742,8 +761,11 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
   ProfScope prof(s, KC_GROUPNORM);
   groupnorm_stats_kernel<<<grid, 256, 0, s>>>(q, pix_per_block);
   DYF_LAUNCH_OK("groupnorm_stats_kernel");
+  float* ab = p.stats + (size_t)p.rows * p.G * GN_SLABS * 2;  // [rows][2][C] behind the slab partials (see gn_scratch_floats)
+  groupnorm_fold_kernel<<<p.rows, 256, 0, s>>>(q, ab);
+  DYF_LAUNCH_OK("groupnorm_fold_kernel");
   const long long total = (long long)p.rows * p.HW * chunks;
-  groupnorm_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(q);
+  groupnorm_apply_kernel<<<cdiv(total, 256), 256, 0, s>>>(q, ab);
   DYF_LAUNCH_OK("groupnorm_apply_kernel");
   return 0;
 }

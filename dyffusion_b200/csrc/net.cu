@@ -130,7 +130,7 @@ int Net::build() {
   stats_floats_per_row = 0;
   for (auto& n : norms) {
     n.stats_off = stats_floats_per_row;
-    stats_floats_per_row += 2 * n.G * 32;
+    stats_floats_per_row += gn_scratch_floats(n.C, n.G);
     if (n.tw >= 0) {
       TimeLayer L{};
       L.w_off = params[n.tw].off;

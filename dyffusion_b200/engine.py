@@ -75,6 +75,7 @@ def _load() -> C.CDLL:
         "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, vp, sz, vp]),
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
         "dyf_profile_enable": (C.c_int, [i32]),
+        "dyf_profile_filter": (C.c_int, [i32]),
         "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(u64), i32]),
     }
@@ -91,7 +92,7 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_net_set_param", "dyf_net_finalize", "dyf_net_num_params", "dyf_net_param_key", "dyf_net_param_shape",
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
-            "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_read"]
+            "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
                   "attention", "conv_up"]
 
@@ -116,6 +117,11 @@ def launch_count() -> int:
 
 def profile_enable(on: bool) -> None:
     _check(LIB.dyf_profile_enable(int(bool(on))))
+
+
+def profile_filter(kernel_class: Optional[str]) -> None:
+    """Bracket only launches of `kernel_class` with events (None = every class)."""
+    _check(LIB.dyf_profile_filter(-1 if kernel_class is None else KERNEL_CLASSES.index(kernel_class)))
 
 
 def profile_read() -> Dict[str, Dict[str, float]]:

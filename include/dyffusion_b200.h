@@ -93,6 +93,9 @@ uint64_t dyf_launch_count(void);
 enum { DYF_KC_CONV_MMA = 0, DYF_KC_CONV_UMMA, DYF_KC_PACK, DYF_KC_UPSAMPLE, DYF_KC_GROUPNORM, DYF_KC_READOUT,
        DYF_KC_TIME, DYF_KC_ELEMENTWISE, DYF_KC_ATTENTION, DYF_KC_CONV_UP, DYF_KC_COUNT };
 int dyf_profile_enable(int32_t on);
+/* Restrict the event bracketing to one kernel class (DYF_KC_*; -1 = all classes): lets bench.py time its dominant kernel
+ * live inside the timed region without putting event records between every other pair of launches. */
+int dyf_profile_filter(int32_t klass);
 int dyf_profile_read(double* ms, double* flops, double* bytes, uint64_t* launches, int32_t n_classes);
 
 /* Replaces: `hydra.utils.instantiate(model_config, ...)` -> backbone constructor
