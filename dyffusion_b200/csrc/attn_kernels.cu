@@ -26,16 +26,55 @@ __device__ __forceinline__ bool keep1(const DropCfg& d, uint64_t elem) {
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
 // y = (x - mean_c) * rsqrt(var_c + 1e-5) * g  per pixel (biased variance, gain only), then the dropout that sits on
-// the input of the qkv projection.  One warp per pixel, C/32 channels per lane.
-template <int PER>
+// the input of the qkv projection.  LANES = C / 8 lanes per pixel, 8 channels (one 128-bit access, one Philox draw) per
+// lane; the channel reduction is a butterfly inside the LANES-wide lane group.
+template <int LANES>
 __global__ void __launch_bounds__(256) channel_ln_kernel(const ChannelLNParams p) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = t / LANES;
+  const int c0 = (int)(t % LANES) * 8;
+  const bool active = pix < p.M;  // (inactive lanes still take part in the shuffles)
+  float v[8];
+  if (active) unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix * p.C + c0)), v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)p.C + 1e-5f);
+  if (!active) return;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(p.g + c0) + 1);
+  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j];
+  if (p.drop.thresh) {
+    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pix * p.C + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop.scale : 0.f;
+  }
+  *reinterpret_cast<uint4*>(p.y + (size_t)pix * p.C + c0) = pack8(v);
+}
+
+// C = 512 (one warp per pixel, 16 channels per lane): the shape outside the shipped configs, kept simple
+__global__ void __launch_bounds__(256) channel_ln_wide_kernel(const ChannelLNParams p) {
+  constexpr int PER = 16;
   const int lane = threadIdx.x & 31;
   const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pix >= p.M) return;
   const __nv_bfloat16* x = p.x + (size_t)pix * p.C + lane * PER;
   float v[PER];
-#pragma unroll
-  for (int j = 0; j < PER; ++j) v[j] = __bfloat162float(x[j]);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x)), v);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x) + 1), v + 8);
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < PER; ++j) s += v[j];
@@ -44,12 +83,17 @@ __global__ void __launch_bounds__(256) channel_ln_kernel(const ChannelLNParams p
 #pragma unroll
   for (int j = 0; j < PER; ++j) { const float d = v[j] - mean; q += d * d; }
   const float rstd = rsqrtf(warp_sum(q) / (float)p.C + 1e-5f);
-  __nv_bfloat16* y = p.y + (size_t)pix * p.C + lane * PER;
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    float o = (v[j] - mean) * rstd * __ldg(p.g + lane * PER + j);
-    if (p.drop.thresh) o = keep1(p.drop, (uint64_t)pix * p.C + lane * PER + j) ? o * p.drop.scale : 0.f;
-    y[j] = __float2bfloat16_rn(o);
+  for (int half = 0; half < 2; ++half) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[8 * half + j] - mean) * rstd * __ldg(p.g + lane * PER + 8 * half + j);
+    if (p.drop.thresh) {
+      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pix * p.C + lane * PER + 8 * half);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * p.drop.scale : 0.f;
+    }
+    reinterpret_cast<uint4*>(p.y + (size_t)pix * p.C + lane * PER)[half] = pack8(o);
   }
 }
 
@@ -249,12 +293,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
 
 int launch_channel_ln(const ChannelLNParams& p, cudaStream_t s) {
   ProfScope prof(s, KC_ATTENTION);
-  const int grid = cdiv(p.M * 32, 256);
+  const int lanes = p.C / 8;
+  const int grid = cdiv(p.M * lanes, 256);
   switch (p.C) {
-    case 64: channel_ln_kernel<2><<<grid, 256, 0, s>>>(p); break;
-    case 128: channel_ln_kernel<4><<<grid, 256, 0, s>>>(p); break;
-    case 256: channel_ln_kernel<8><<<grid, 256, 0, s>>>(p); break;
-    case 512: channel_ln_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    case 64: channel_ln_kernel<8><<<grid, 256, 0, s>>>(p); break;
+    case 128: channel_ln_kernel<16><<<grid, 256, 0, s>>>(p); break;
+    case 256: channel_ln_kernel<32><<<grid, 256, 0, s>>>(p); break;
+    case 512: channel_ln_wide_kernel<<<cdiv(p.M * 32, 256), 256, 0, s>>>(p); break;
     default: set_error("channel LayerNorm: channel count must be 64, 128, 256 or 512"); return -1;
   }
   DYF_LAUNCH_OK("channel_ln_kernel");
