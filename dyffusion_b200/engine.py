@@ -74,6 +74,8 @@ def _load() -> C.CDLL:
         "dyf_sampler_num_outputs": (C.c_int, [vp, C.POINTER(i32), C.POINTER(C.c_double), i32]),
         "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, vp, sz, vp]),
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
+        "dyf_ensemble_metrics_workspace_bytes": (C.c_int, [i32, C.c_int64, C.c_int64, C.POINTER(sz)]),
+        "dyf_ensemble_metrics": (C.c_int, [vp, vp, i32, C.c_int64, C.c_int64, vp, vp, vp, sz, vp]),
         "dyf_profile_enable": (C.c_int, [i32]),
         "dyf_profile_filter": (C.c_int, [i32]),
         "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -92,7 +94,8 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_net_set_param", "dyf_net_finalize", "dyf_net_num_params", "dyf_net_param_key", "dyf_net_param_shape",
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
-            "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read"]
+            "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read",
+            "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
                   "attention", "conv_up"]
 
@@ -130,6 +133,22 @@ def profile_read() -> Dict[str, Dict[str, float]]:
     ms, fl, by, la = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
     _check(LIB.dyf_profile_read(ms, fl, by, la, n))
     return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(la[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+
+def ensemble_metrics(preds: torch.Tensor, targets: torch.Tensor, per_member: bool = False):
+    """preds [members, samples, inner] / targets [samples, inner], fp32 CUDA -> (per_sample [samples, 3] float64 sums of
+    crps / squared error of the ensemble mean / member variance over `inner`, per_member_mse [members] float64 or None)."""
+    preds = _require_cuda(preds, "predictions").contiguous()
+    targets = _require_cuda(targets, "targets").contiguous()
+    n, s, d = preds.shape
+    nbytes = C.c_size_t()
+    _check(LIB.dyf_ensemble_metrics_workspace_bytes(n, s, d, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=preds.device)
+    per_sample = torch.empty((s, 3), dtype=torch.float64, device=preds.device)
+    member = torch.empty((n,), dtype=torch.float64, device=preds.device) if per_member else None
+    _check(LIB.dyf_ensemble_metrics(preds.data_ptr(), targets.data_ptr(), n, s, d, per_sample.data_ptr(),
+                                    member.data_ptr() if per_member else None, ws.data_ptr(), nbytes.value, _stream_ptr()))
+    return per_sample, member
 
 
 def _stream_ptr() -> int:

@@ -170,6 +170,20 @@ int dyf_sampler_num_outputs(const dyf_sampler* s, int32_t* n_outputs, double* ke
 int dyf_sampler_run(dyf_sampler* s, int32_t rows, const float* ic, const float* static_cond, float* preds,
                     float* x0_hat_out, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Widening row SURVEY.md 8f-2 -- on-device ensemble evaluation.
+ * Replaces: `evaluate_ensemble_prediction` (src/utilities/evaluation.py:10-80), `evaluate_ensemble_crps` (:83-97, i.e.
+ * xskillscore.crps_ensemble with equal member weights) and `evaluate_ensemble_spread_skill_ratio` (:100-120), which the
+ * reference feeds with numpy copies of every horizon (src/experiment_types/forecasting_multi_horizon.py:185-187, :246).
+ * preds: [n_members, n_samples, inner] fp32 (device), targets: [n_samples, inner]; `inner` = product of the remaining
+ * dimensions.  per_sample (device, [n_samples][3] doubles) receives, per sample, the SUMS over `inner` of: the CRPS, the
+ * squared error of the ensemble mean, the population variance over members -- the host finishes
+ * crps = sum/inner, mse = sum/inner, ssr = sqrt(mean var) / sqrt(mse) for either setting of `mean_over_samples`.
+ * per_member_mse (device, [n_members] doubles, may be NULL): mean squared error of every member (:47-53).
+ * Sums are accumulated in a fixed order (bit-reproducible). */
+int dyf_ensemble_metrics_workspace_bytes(int32_t n_members, int64_t n_samples, int64_t inner, size_t* bytes);
+int dyf_ensemble_metrics(const float* preds, const float* targets, int32_t n_members, int64_t n_samples, int64_t inner,
+                         double* per_sample, double* per_member_mse, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hook: writes the keep-mask (1/0 bytes) the engine's dropout draws for a tensor of `n_elems` elements
  * (NHWC element order, channel count `channels`) at (seed, stream, site, p).  Lets tests replay engine masks in
  * the oracle. */
