@@ -1,0 +1,48 @@
+"""On-device drop-in for the benchmark's boundary conditions:
+`PhysicalSystemsBenchmarkDataModule.boundary_conditions` (`src/datamodules/physical_systems_benchmark.py:245-297`) loops
+over the batch in Python doing masked writes; here it is one kernel launch.  Same arguments, same in-place semantics and
+return value, same error for unknown systems.  No CPU / PyTorch fallback."""
+from __future__ import annotations
+
+import torch
+
+from . import engine as E
+
+
+def boundary_conditions(physical_system: str, preds: torch.Tensor, targets: torch.Tensor, metadata, time=None) -> torch.Tensor:
+    """`physical_system` is the datamodule's `hparams.physical_system`; the rest mirrors the reference signature."""
+    batch_size = targets.shape[0]
+    if not preds.is_cuda:
+        raise E.EngineError("dyffusion_b200.boundary has no CPU path: `preds` must be a CUDA tensor")
+    if not (preds.is_contiguous() and preds.dtype == torch.float32):
+        raise ValueError("preds must be a contiguous float32 tensor (it is updated in place)")
+    dev = preds.device
+    if physical_system == "navier-stokes":
+        if preds.ndim != 4 or preds.shape[0] != batch_size:
+            raise ValueError("navier-stokes boundary conditions expect preds of shape (batch, 3, H, W)")
+        b, c, h, w = preds.shape
+        mask = metadata["fixed_mask"].to(dev)
+        assert tuple(mask.shape[1:]) == (c, h, w), f"fixed_mask={tuple(mask.shape[1:])}, predictions={tuple(preds.shape)}"
+        mask = mask.to(torch.uint8).contiguous()
+        vy = metadata["vertices"][:, 1, 0, :].to(dev, torch.float32).contiguous()
+        vel = metadata["in_velocity"].reshape(batch_size).to(dev, torch.float32).contiguous()
+        per_sample = not isinstance(time, float)
+        t = (time.reshape(batch_size) if per_sample else torch.tensor([time])).to(dev, torch.float32).contiguous()
+        E._check(E.LIB.dyf_boundary_conditions_navier_stokes(preds.data_ptr(), mask.data_ptr(), vy.data_ptr(), vel.data_ptr(),
+                                                           t.data_ptr(), int(per_sample), b, c, h, w, E._stream_ptr()))
+    elif physical_system == "spring-mesh":
+        mask = metadata["fixed_mask"].to(dev)
+        assert mask.shape[1] == 4, f"fixed_mask_pq={tuple(mask.shape[1:])}, should be (4, 10, 10)"
+        if preds.ndim == 5 and preds.shape[1] == batch_size:
+            lead = preds.shape[0]
+        elif preds.ndim == 4 and preds.shape[0] == batch_size:
+            lead = 1
+        else:
+            raise ValueError("spring-mesh boundary conditions expect preds of shape ([members,] batch, 4, H, W)")
+        h, w = preds.shape[-2:]
+        base_q = metadata["features"][:, 0, 2:].to(dev, torch.float32).contiguous()
+        E._check(E.LIB.dyf_boundary_conditions_spring_mesh(preds.data_ptr(), mask.to(torch.uint8).contiguous().data_ptr(),
+                                                         base_q.data_ptr(), lead, batch_size, h, w, E._stream_ptr()))
+    else:
+        raise NotImplementedError(f"Boundary conditions for {physical_system} not implemented")
+    return preds

@@ -168,3 +168,85 @@ int dyf_ensemble_metrics(const float* preds, const float* targets, int32_t n_mem
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Boundary conditions of the physical-systems benchmark on device (reference:
+// src/datamodules/physical_systems_benchmark.py:245-297, a per-sample Python loop of masked writes).
+namespace dyf {
+namespace {
+
+// Navier-Stokes (:253-276): preds[b, c, h, w] = 0 where fixed_mask[b, c, h, w]; then the parabolic inflow profile on
+// channel 0, first grid row: in_velocity * 4 * y * (0.41 - y) / 0.41^2 * (1 - exp(-5 t)), y = vertex_y[b, w].
+__global__ void bc_navier_stokes_kernel(float* __restrict__ preds, const uint8_t* __restrict__ mask, const float* __restrict__ vertex_y,
+                                        const float* __restrict__ in_velocity, const float* __restrict__ time, int time_stride,
+                                        int B, int C, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)C * H * W;
+  if (idx >= (long long)B * per) return;
+  const int b = (int)(idx / per);
+  const long long e = idx - (long long)b * per;
+  const int w = (int)(e % W), h = (int)((e / W) % H), c = (int)(e / ((long long)W * H));
+  float v = preds[idx];
+  if (mask[idx]) v = 0.f;
+  if (c == 0 && h == 0) {
+    const float y = vertex_y[(size_t)b * W + w];
+    const float t = time[(size_t)b * time_stride];
+    float p = in_velocity[b] * 4.f;          // same operation order as the reference's fp32 tensor expression
+    p = p * y;
+    p = p * (0.41f - y);
+    p = p / (float)(0.41 * 0.41);
+    p = p * (float)(1.0 - exp(-5.0 * (double)t));
+    v = p;
+  }
+  preds[idx] = v;
+}
+
+// spring-mesh (:277-287): preds[(e,) b] = where(fixed_mask[b], boundary[b], preds[(e,) b]); boundary = cat(0, base_q)
+__global__ void bc_spring_mesh_kernel(float* __restrict__ preds, const uint8_t* __restrict__ mask, const float* __restrict__ base_q,
+                                      long long lead, int B, int HW) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = 4LL * HW;
+  if (idx >= lead * B * per) return;
+  const int b = (int)((idx / per) % B);
+  const long long e = idx % per;
+  const int c = (int)(e / HW);
+  if (mask[(size_t)b * per + e]) preds[idx] = c < 2 ? 0.f : base_q[((size_t)b * 2 + (c - 2)) * HW + (e % HW)];
+}
+
+}  // namespace
+}  // namespace dyf
+
+extern "C" {
+
+int dyf_boundary_conditions_navier_stokes(float* preds, const uint8_t* fixed_mask, const float* vertex_y, const float* in_velocity,
+                                          const float* time, int32_t time_per_sample, int32_t batch, int32_t channels,
+                                          int32_t height, int32_t width, void* stream) {
+  if (!preds || !fixed_mask || !vertex_y || !in_velocity || !time || batch < 1 || channels < 1 || height < 1 || width < 1) {
+    set_error("null or empty argument");
+    return DYF_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: dyffusion_b200 has no CPU fallback"); return DYF_ERR_CUDA; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)batch * channels * height * width;
+  ProfScope prof(s, KC_ELEMENTWISE);
+  bc_navier_stokes_kernel<<<cdiv(total, 256), 256, 0, s>>>(preds, fixed_mask, vertex_y, in_velocity, time, time_per_sample ? 1 : 0,
+                                                         batch, channels, height, width);
+  DYF_LAUNCH_OK("bc_navier_stokes_kernel");
+  return 0;
+}
+
+int dyf_boundary_conditions_spring_mesh(float* preds, const uint8_t* fixed_mask, const float* base_q, int64_t lead, int32_t batch,
+                                        int32_t height, int32_t width, void* stream) {
+  if (!preds || !fixed_mask || !base_q || lead < 1 || batch < 1 || height < 1 || width < 1) { set_error("null or empty argument"); return DYF_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: dyffusion_b200 has no CPU fallback"); return DYF_ERR_CUDA; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = lead * batch * 4LL * height * width;
+  ProfScope prof(s, KC_ELEMENTWISE);
+  bc_spring_mesh_kernel<<<cdiv(total, 256), 256, 0, s>>>(preds, fixed_mask, base_q, lead, batch, height * width);
+  DYF_LAUNCH_OK("bc_spring_mesh_kernel");
+  return 0;
+}
+
+}  // extern "C"

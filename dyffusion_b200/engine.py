@@ -76,6 +76,8 @@ def _load() -> C.CDLL:
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
         "dyf_ensemble_metrics_workspace_bytes": (C.c_int, [i32, C.c_int64, C.c_int64, C.POINTER(sz)]),
         "dyf_ensemble_metrics": (C.c_int, [vp, vp, i32, C.c_int64, C.c_int64, vp, vp, vp, sz, vp]),
+        "dyf_boundary_conditions_navier_stokes": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "dyf_boundary_conditions_spring_mesh": (C.c_int, [vp, vp, vp, C.c_int64, i32, i32, i32, vp]),
         "dyf_profile_enable": (C.c_int, [i32]),
         "dyf_profile_filter": (C.c_int, [i32]),
         "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -95,7 +97,8 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
             "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read",
-            "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics"]
+            "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics", "dyf_boundary_conditions_navier_stokes",
+            "dyf_boundary_conditions_spring_mesh"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
                   "attention", "conv_up"]
 

@@ -184,6 +184,20 @@ int dyf_ensemble_metrics_workspace_bytes(int32_t n_members, int64_t n_samples, i
 int dyf_ensemble_metrics(const float* preds, const float* targets, int32_t n_members, int64_t n_samples, int64_t inner,
                          double* per_sample, double* per_member_mse, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Widening row SURVEY.md 8f-3 (first half) -- the benchmark's boundary conditions as one masked-write kernel.
+ * Replaces: `PhysicalSystemsBenchmarkDataModule.boundary_conditions` (src/datamodules/physical_systems_benchmark.py:245-297),
+ * a per-sample Python loop.  In place on `preds`.
+ * Navier-Stokes (:253-276): preds [batch, channels, H, W]; fixed_mask [batch, channels, H, W] (bytes, non-zero = fixed ->
+ * 0); then channel 0 / grid row 0 <- in_velocity[b] * 4 y (0.41 - y) / 0.41^2 * (1 - exp(-5 t)), y = vertex_y[b, w]
+ * (vertex_y = metadata["vertices"][:, 1, 0, :]); time: one value (time_per_sample = 0) or [batch].
+ * spring-mesh (:277-287): preds [lead, batch, 4, H, W] (lead = 1 or the ensemble size); fixed_mask [batch, 4, H, W];
+ * base_q [batch, 2, H, W] (= metadata["features"][:, 0, 2:]); fixed p <- 0, fixed q <- base_q. */
+int dyf_boundary_conditions_navier_stokes(float* preds, const uint8_t* fixed_mask, const float* vertex_y, const float* in_velocity,
+                                          const float* time, int32_t time_per_sample, int32_t batch, int32_t channels,
+                                          int32_t height, int32_t width, void* stream);
+int dyf_boundary_conditions_spring_mesh(float* preds, const uint8_t* fixed_mask, const float* base_q, int64_t lead, int32_t batch,
+                                        int32_t height, int32_t width, void* stream);
+
 /* Test hook: writes the keep-mask (1/0 bytes) the engine's dropout draws for a tensor of `n_elems` elements
  * (NHWC element order, channel count `channels`) at (seed, stream, site, p).  Lets tests replay engine masks in
  * the oracle. */
