@@ -197,5 +197,5 @@ def install() -> None:
     _mod("xskillscore")
     _mod("dask")
     if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+        sys.path.append(REFERENCE_ROOT)  # at the END: the reference has its own (empty) `tests` package
     install._done = True
