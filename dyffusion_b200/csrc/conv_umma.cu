@@ -2,23 +2,26 @@
 // weights streamed by bulk-TMA (cp.async.bulk + mbarrier complete_tx) and the activations staged ONCE per channel
 // chunk as a halo patch that every filter tap re-reads through shifted UMMA shared-memory descriptors.
 //
-// Tile: 16 x 8 output pixels (M = 128) x BN output channels.  Two geometries share one kernel:
-//   S1K3  3x3, stride 1, pad 1 (decoder):  64-channel chunks, patch 18 x 10 pixels, 9 taps
-//   S2K4  4x4, stride 2, pad 1 (encoder):  32-channel chunks, patch 34 x 18 pixels split by column parity, 16 taps
-// A patch is stored K-major / no-swizzle as 16-byte channel planes [plane][pixel], so that
-//   * 8 consecutive M rows (one UMMA core matrix) = 8 consecutive pixels of a patch row        (16 B apart),
-//   * consecutive 8-row groups = consecutive (S1) / every other (S2) patch row                 (SBO),
-//   * the two 16-byte K halves of a K=16 step = consecutive channel planes                     (LBO = plane stride),
-// and a tap (ky, kx) is nothing but a start-address offset.  For stride 2 the patch columns are de-interleaved by
-// parity while they are gathered, which turns the stride-2 pixel walk of a tap into a unit-stride one.
-// Activations therefore cross L2 -> SM once (x1.4 halo for 3x3) instead of once per tap, which is what lets the
-// N = 64 / 128 layers (most of the Navier-Stokes FLOPs) feed the tensor pipe.  Zero padding = zero-filled cp.async.
+// Tile: 16 x 8 output pixels (M = 128) x BN output channels; T tiles side by side share every weight stage (L2 -> SM
+// bandwidth, ~42 B/cycle/SM, is what a 128-row tile cannot afford to spend on its own weight stream).  Modes:
+//   S1K3  3x3, stride 1, pad 1:  64-channel chunks; the patch of the 16 x 8T super-tile is ONE 4-D tensor-map box
+//         (cp.async.bulk.tensor, 128-byte swizzle, hardware zero fill = padding); a tap is a start-address shift of
+//         (ky * patch_width + kx) * 128 B of a SWIZZLE_128B K-major descriptor whose SBO is one patch row
+//   S2K4  4x4, stride 2, pad 1:  32-channel chunks; four boxes, one per (row parity, column parity) VIEW of the input
+//         (tensor maps with pixel/row pitch 2), 64-byte swizzle: inside a view the stride-2 walk is unit stride and
+//         tap (ky, kx) is a shift of (ky>>1, kx>>1) inside view ((ky+1)&1, (kx+1)&1)
+//   S1K1  1x1: the 16 x 8T pixel box itself, one "tap"
+//   S2K2  2x2, stride 2, pad 0:  runs on the S1K1 kernel over two strided tensor-map views of the input (a free
+//         space-to-depth): K = (ky, kx, ci)
+// A cp.async gather path (K-major / no-swizzle 16-byte channel planes [plane][pixel]; 8 gather warps) is kept for every
+// mode as the fallback when no tensor map can be built and as the bit-exact A/B reference (DYF_UMMA_A=cpasync).
 //
-// Persistent, warp-specialised CTA (448 threads, one per SM): warps 0-7 run the epilogue (tcgen05.ld -> fused affine /
-// activation / dropout / residual -> 128-bit stores), warps 8-11 gather patches (cp.async, completion signalled
-// straight to an mbarrier), warp 12 owns TMEM and issues the MMAs (one thread), warp 13 streams weight tiles.
-// Two TMEM accumulators ping-pong, so the epilogue of tile i overlaps the MMAs of tile i+1 and the A/B rings
-// (3-4 patch stages, 6-8 weight stages, all on mbarriers) keep streaming across tile boundaries.
+// Persistent, warp-specialised CTA (one per SM): warps 0-7 run the epilogue (tcgen05.ld.x32 -> per-item tables from
+// shared memory -> fused affine / activation / dropout / residual as straight-line 32-column blocks -> 128-bit stores),
+// then the patch producer (one TMA-issuing thread, or 8 cp.async warps), the MMA warp (owns TMEM, one elected thread
+// issues) and the weight-stream warp.  Two TMEM accumulator sets ping-pong, so the epilogue of item i overlaps the MMAs
+// of item i+1 and the A/B rings (2-6 patch stages, 4-9 weight stages, all on mbarriers) keep streaming across items.
+// Work items go round-robin over the CTAs (concurrent CTAs on neighbouring tiles), in runs of 8 for single-chunk layers.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -475,8 +478,8 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
 // Pipeline shapes that fill the 227 KB of one SM.  T = pixel tiles per work item (TMA mode), GT = taps per weight stage,
 // A / B = patch / weight ring depths.
 // V = shape variant: 0 = default; 1 = single-chunk layers (Cin == one chunk, one n-tile, e.g. the NS stem): the whole
-// filter stays resident in the weight ring and the freed L2 bandwidth + a deeper patch ring feed the short tiles;
-// 2, 3 = experiment shapes of the stride-2 kernel (DYF_S2K4_CFG).
+// filter stays resident in the weight ring and the freed L2 bandwidth + a deeper patch ring feed the short tiles; also the
+// single-tile shape of 1x1 convs on grids <= 8 pixels wide.
 template <int MODE, int BN, bool TMA, int V = 0> struct Stages;
 template <> struct Stages<S1K3, 64, true> { static constexpr int T = 2, GT = 1, A = 3, B = 9; };    // 123 KB patches +  72 KB weights
 template <> struct Stages<S1K3, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   //  82 KB patches + 128 KB weights
@@ -494,8 +497,6 @@ template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2,
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
 template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };    // 152 KB views +  64 KB weights
 template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   // 152 KB views +  64 KB weights
-template <> struct Stages<S2K4, 128, false, 2> { static constexpr int T = 1, GT = 1, A = 2, B = 17; };  //  77 KB patches + 136 KB weights
-template <> struct Stages<S2K4, 128, false, 3> { static constexpr int T = 1, GT = 1, A = 4, B = 8; };   // 154 KB patches +  64 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
 static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
@@ -656,9 +657,6 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     }
     if (ok) return n64 ? launch_t<64, S2K4, true>(p, stream, it->second.m) : launch_t<128, S2K4, true>(p, stream, it->second.m);
   }
-  static const char* env_c = getenv("DYF_S2K4_CFG");
-  if (!n64 && env_c && env_c[0] == '2') return launch_t<128, S2K4, false, 2>(p, stream);
-  if (!n64 && env_c && env_c[0] == '3') return launch_t<128, S2K4, false, 3>(p, stream);
   return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
 }
 

@@ -1,6 +1,7 @@
 """Profiling driver: two Navier-Stokes interpolator forwards (dropout on) through the engine; used under ncu."""
 import sys
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 from tests.gpu_helpers import build_backbone
 from oracle.synth import synth_tensor

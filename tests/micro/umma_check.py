@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 from dyffusion_b200.backbones import SimpleConvNet
 from oracle.synth import synth_state_dict, synth_tensor
