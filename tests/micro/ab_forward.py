@@ -15,9 +15,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--save")
 ap.add_argument("--compare")
 ap.add_argument("--dataset", default="ns")
+ap.add_argument("--rows", type=int, default=3)
 a = ap.parse_args()
 net = build_backbone(a.dataset, "I", seed=1)
-rows = 3
+rows = a.rows
 x, c = H.forward_inputs(a.dataset, "I", rows=rows)
 t = torch.linspace(1.0, 3.0, rows).cuda()
 with torch.no_grad():
