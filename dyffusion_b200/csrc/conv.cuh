@@ -8,6 +8,8 @@ namespace dyf {
 
 struct ConvParams {
   const __nv_bfloat16* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
+  const __nv_bfloat16* in2;  // optional second source [rows, Hi, Wi, Cin - Cin0]: the input is the channel concat
+  int Cin0;                  //   [in | in2] without a concat buffer (tcgen05 TMA path only); 0 = single source
   const __nv_bfloat16* w_umma;  // weights re-packed as UMMA stage tiles (conv_umma.cu) or nullptr
   const __nv_bfloat16* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
   void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32

@@ -499,14 +499,14 @@ template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 2, 
 template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   // 152 KB views +  64 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
-static int make_patch_tmap(const ConvParams& p, int pw, int ph, CUtensorMap* out) {
+static int make_patch_tmap(const ConvParams& p, const __nv_bfloat16* src, int C, int pw, int ph, CUtensorMap* out) {
   using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
-  const Key key{p.in, p.rows, p.Hi, p.Wi, p.Cin, pw, ph};
+  const Key key{src, p.rows, p.Hi, p.Wi, C, pw, ph};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return 0; }
   CUtensorMap m;
-  if (make_nhwc_tmap(p.in, p.rows, p.Hi, p.Wi, p.Cin, p.Cin, pw, ph, 1, &m) != 0) return -1;
+  if (make_nhwc_tmap(src, p.rows, p.Hi, p.Wi, C, C, pw, ph, 1, &m) != 0) return -1;
   if (cache.size() > 4096) cache.clear();
   cache[key] = m;
   *out = m;
@@ -533,7 +533,12 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   }
   CUtensorMap tmap{}, tmap2{}, tmap3{}, tmap4{};
   if (views) { tmap = views[0]; tmap2 = views[1]; if (MODE == S2K4) { tmap3 = views[2]; tmap4 = views[3]; } }
-  else if (TMA && make_patch_tmap(p, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
+  else if (TMA && p.in2) {  // channel concat of two sources: chunks [0, Cin0/64) from the first map, the rest from the second
+    if (make_patch_tmap(p, p.in, p.Cin0, TILE_W * T + G::HALO, G::PH, &tmap) != 0 ||
+        make_patch_tmap(p, p.in2, p.Cin - p.Cin0, TILE_W * T + G::HALO, G::PH, &tmap2) != 0)
+      return 0;
+    nch_split = p.Cin0 / G::CH;
+  } else if (TMA && make_patch_tmap(p, p.in, p.Cin, TILE_W * T + G::HALO, G::PH, &tmap) != 0) return 0;  // caller falls back
   const int tiles_x = (p.Wo + TILE_W * T - 1) / (TILE_W * T), tiles_y = (p.Ho + TILE_H - 1) / TILE_H;
   const int n_tiles = (p.Cout + BN - 1) / BN;
   const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
@@ -571,6 +576,10 @@ bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad) {
 }
 
 bool conv_umma_eligible(const ConvParams& p) {
+  if (p.in2) {  // two-source input: stride-1 TMA modes only, both parts whole chunks
+    const int mode = mode_of(p.KH, p.stride, p.pad);
+    if ((mode != S1K3 && mode != S1K1) || p.Cin0 <= 0 || p.Cin0 % 64 || (p.Cin - p.Cin0) % 64) return false;
+  }
   return p.w_umma != nullptr && p.KH == p.KW && conv_umma_shape_ok(p.Cin, p.Cout, p.KH, p.stride, p.pad) &&
          p.out_fp32 == 0 && ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
 }
@@ -619,19 +628,20 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   const bool want_tma = !(env_a && env_a[0] == 'c');
   // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
   //  and UMMA reads alike -- verified on hardware)
+  if (p.in2 && !want_tma) return 0;
   if (mode == S1K3) {
     if (want_tma) {
       const bool single = p.Cin == 64 && p.Cout <= 128;  // one chunk, one n-tile: resident filter
       const int rc = n64 ? launch_t<64, S1K3, true>(p, stream)
                          : single ? launch_t<128, S1K3, true, 1>(p, stream) : launch_t<128, S1K3, true>(p, stream);
-      if (rc != 0) return rc;
+      if (rc != 0 || p.in2) return rc;
     }
     return n64 ? launch_t<64, S1K3, false>(p, stream) : launch_t<128, S1K3, false>(p, stream);
   }
   if (mode == S1K1) {
     if (want_tma) {
       const int rc = n64 ? launch_t<64, S1K1, true>(p, stream) : launch_t<128, S1K1, true>(p, stream);
-      if (rc != 0) return rc;
+      if (rc != 0 || p.in2) return rc;
     }
     return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
   }

@@ -104,7 +104,7 @@ struct Net {
   int build_unet_simple();
   int build_convnet();
   int build_unet_resnet();
-  int resnet_block(const std::string& prefix, int x, int Cin, int Cout, int& site);
+  int resnet_block(const std::string& prefix, int x, int Cin, int Cout, int& site, int x2 = BUF_NONE);  // x2: second source of a channel concat [x | x2] that is never materialised
   int attention_block(const std::string& prefix, int x, int C, bool linear, int& site);
   int add_conv(const std::string& wkey, int Cin, int Cout, int k, int stride, int pad, bool bias = true);
   void attach_bn(ConvLayer& c, const std::string& prefix);

@@ -339,7 +339,7 @@ int Net::build_convnet() {
 // ---------------------------------------------------------------------------------------------------------------
 // ResnetBlock (unet.py:79-109): block1 = WS-conv3x3 -> GroupNorm -> x*(scale+1)+shift -> SiLU -> Dropout(p1),
 // block2 = WS-conv3x3 -> GroupNorm -> SiLU -> Dropout(p2), output = block2 + residual_conv(x).
-int Net::resnet_block(const std::string& P, int x, int Cin, int Cout, int& site) {
+int Net::resnet_block(const std::string& P, int x, int Cin, int Cout, int& site, int x2) {
   const int H = bufs[x].H, W = bufs[x].W;
   int tw = -1, tb = -1;
   attach_time(tw, tb, P + ".mlp.1", Cout);
@@ -348,6 +348,7 @@ int Net::resnet_block(const std::string& P, int x, int Cin, int Cout, int& site)
     convs[li].standardize = true;  // WeightStandardizedConv2d (:26-40), folded once at load time
     int raw = add_buf(H, W, Cout);
     Op c{}; c.type = OP_CONV; c.in0 = in; c.out = raw; c.layer = li; c.act = ACT_NONE;
+    if (in == x) c.in1 = x2;  // block1 of a concat-fed block reads both sources
     ops.push_back(c);
     NormLayer n; n.C = Cout; n.G = d.groups;
     n.g = add_param(blk + ".norm.weight", {Cout});
@@ -375,7 +376,7 @@ int Net::resnet_block(const std::string& P, int x, int Cin, int Cout, int& site)
   if (Cin != Cout) {  // 1x1 residual projection (:96)
     int li = add_conv(P + ".residual_conv", Cin, Cout, 1, 1, 0);
     res = add_buf(H, W, Cout);
-    Op c{}; c.type = OP_CONV; c.in0 = x; c.out = res; c.layer = li; c.act = ACT_NONE;
+    Op c{}; c.type = OP_CONV; c.in0 = x; c.in1 = x2; c.out = res; c.layer = li; c.act = ACT_NONE;
     ops.push_back(c);
   }
   int y = add_buf(H, W, Cout);
@@ -447,6 +448,14 @@ int Net::build_unet_resnet() {
   x = resnet_block("mid_block1", x, mid, mid, site);
   x = attention_block("mid_attn", x, mid, false, site);
   x = resnet_block("mid_block2", x, mid, mid, site);
+  // cat(a, b) feeding a ResnetBlock needs no buffer when both of its readers (block1's 3x3 conv and the 1x1 residual
+  // conv) run on the tcgen05 TMA path, which reads the K axis from two tensor maps (DYF_DISABLE_CATFUSE=1: always copy)
+  auto cat_free = [&](int a, int b, int Cout) {
+    const int Ca = bufs[a].C, Cb = bufs[b].C;
+    return bufs[a].H == bufs[b].H && bufs[a].W == bufs[b].W && Ca % 64 == 0 && Cb % 64 == 0 && Ca + Cb != Cout &&
+           conv_umma_shape_ok(Ca + Cb, Cout, 3, 1, 1) && conv_umma_shape_ok(Ca + Cb, Cout, 1, 1, 0) &&
+           !getenv("DYF_DISABLE_CATFUSE") && !getenv("DYF_DISABLE_UMMA");
+  };
   auto concat = [&](int a, int b) {
     if (bufs[a].H != bufs[b].H || bufs[a].W != bufs[b].W) return -1;
     int y = add_buf(bufs[a].H, bufs[a].W, bufs[a].C + bufs[b].C);
@@ -458,10 +467,15 @@ int Net::build_unet_resnet() {
     const int din = dims[nres - 1 - l], dout = dims[nres - l];
     const std::string P = "ups." + std::to_string(l);
     for (int j = 0; j < 2; ++j) {
-      int cat = concat(x, hs.back());
+      const int skip = hs.back();
       hs.pop_back();
-      if (cat < 0) { set_error("Unet: skip connection grid mismatch (odd spatial size; reference fails too, SURVEY.md F4)"); return DYF_ERR_UNSUPPORTED; }
-      x = resnet_block(P + "." + std::to_string(j), cat, dout + din, dout, site);
+      if (cat_free(x, skip, dout)) {  // both convs that read cat(x, skip) take the two sources directly
+        x = resnet_block(P + "." + std::to_string(j), x, dout + din, dout, site, skip);
+      } else {
+        int cat = concat(x, skip);
+        if (cat < 0) { set_error("Unet: skip connection grid mismatch (odd spatial size; reference fails too, SURVEY.md F4)"); return DYF_ERR_UNSUPPORTED; }
+        x = resnet_block(P + "." + std::to_string(j), cat, dout + din, dout, site);
+      }
     }
     x = attention_block(P + ".2", x, dout, true, site);
     const bool up = l < nres - 1 && !d.keep_spatial_dims;
@@ -477,9 +491,13 @@ int Net::build_unet_resnet() {
     ops.push_back(o);
     x = y;
   }
-  int cat = concat(x, r);
-  if (cat < 0) { set_error("Unet: output grid differs from the stem grid"); return DYF_ERR_UNSUPPORTED; }
-  x = resnet_block("final_res_block", cat, 2 * dim, dim, site);
+  if (cat_free(x, r, dim)) {
+    x = resnet_block("final_res_block", x, 2 * dim, dim, site, r);
+  } else {
+    int cat = concat(x, r);
+    if (cat < 0) { set_error("Unet: output grid differs from the stem grid"); return DYF_ERR_UNSUPPORTED; }
+    x = resnet_block("final_res_block", cat, 2 * dim, dim, site);
+  }
   int fl = add_conv("final_conv", dim, d.out_channels, 1, 1, 0);
   Op f{}; f.type = OP_CONV; f.in0 = x; f.layer = fl; f.out_mode = 2;
   ops.push_back(f);
@@ -721,8 +739,13 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
         if (o.out_mode == 2) { p.out = y; p.out_fp32 = 2; p.out_ld = c.Cout; }
         else { p.out = bp[o.out]; p.out_ld = bufs[o.out].C; p.out_coff = o.out_coff; }
-        if (bi.C != c.Cpad) { set_error("internal: conv input channel mismatch"); return DYF_ERR_STATE; }
+        if (o.in1 >= 0) {  // channel concat [in0 | in1] read in place
+          p.in2 = bp[o.in1]; p.Cin0 = bi.C; p.Cin = bi.C + bufs[o.in1].C;
+          if (!c.flops_cin) p.Cin_real = p.Cin;
+        }
+        if (p.Cin != c.Cpad) { set_error("internal: conv input channel mismatch"); return DYF_ERR_STATE; }
         rc = launch_conv_umma(p, s);
+        if (rc == 0 && p.in2) { set_error("internal: two-source conv needs the tcgen05 TMA path"); return DYF_ERR_STATE; }
         if (rc == 0) rc = launch_conv_mma(p, s);
         else if (rc > 0) rc = 0;
         break;
