@@ -7,14 +7,16 @@
 //   S1K3  3x3, stride 1, pad 1:  64-channel chunks; the patch of the 16 x 8T super-tile is ONE 4-D tensor-map box
 //         (cp.async.bulk.tensor, 128-byte swizzle, hardware zero fill = padding); a tap is a start-address shift of
 //         (ky * patch_width + kx) * 128 B of a SWIZZLE_128B K-major descriptor whose SBO is one patch row
-//   S2K4  4x4, stride 2, pad 1:  32-channel chunks; four boxes, one per (row parity, column parity) VIEW of the input
-//         (tensor maps with pixel/row pitch 2), 64-byte swizzle: inside a view the stride-2 walk is unit stride and
-//         tap (ky, kx) is a shift of (ky>>1, kx>>1) inside view ((ky+1)&1, (kx+1)&1)
+//   S2K4  4x4, stride 2, pad 1:  64-channel chunks; one box per (row parity, column parity) VIEW of the input (tensor
+//         maps with pixel/row pitch 2), 128-byte swizzle: inside a view the stride-2 walk is unit stride and tap (ky, kx)
+//         is a shift of (ky>>1, kx>>1) inside view ((ky+1)&1, (kx+1)&1); the patch ring is view-granular (one stage = one
+//         view of one chunk = 4 taps)
 //   S1K1  1x1: the 16 x 8T pixel box itself, one "tap"
 //   S2K2  2x2, stride 2, pad 0:  runs on the S1K1 kernel over two strided tensor-map views of the input (a free
 //         space-to-depth): K = (ky, kx, ci)
-// A cp.async gather path (K-major / no-swizzle 16-byte channel planes [plane][pixel]; 8 gather warps) is kept for every
-// mode as the fallback when no tensor map can be built and as the bit-exact A/B reference (DYF_UMMA_A=cpasync).
+// A cp.async gather path (K-major / no-swizzle 16-byte channel planes [plane][pixel]; 8 gather warps; 32-channel chunks for
+// stride 2) is kept for every mode as the fallback when no tensor map can be built and as the A/B reference
+// (DYF_UMMA_A=cpasync: bit-exact for stride 1, same sums in another order for stride 2).
 //
 // Persistent, warp-specialised CTA (one per SM): warps 0-7 run the epilogue (tcgen05.ld.x32 -> per-item tables from
 // shared memory -> fused affine / activation / dropout / residual as straight-line 32-column blocks -> 128-bit stores),
@@ -121,21 +123,25 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
   constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
-  constexpr int PLANE = S::PLANE, KSTEPS = S::KSTEPS;
+  constexpr bool S2TMA = TMA && MODE == S2K4;
+  constexpr int CHK = S2TMA ? 64 : G::CH;   // channels per chunk (the stride-2 TMA path uses 64: 128-byte pixel rows)
+  constexpr int PLANE = S::PLANE, KSTEPS = CHK / 16;
   static_assert(TMA || T == 1 || MODE == S2K4, "multi-tile gathered patches: stride-2 mode only");
   static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
   constexpr int PWT = TILE_W * T + G::HALO;  // patch width of the super-tile (TMA mode)
   constexpr int PIXT = G::PH * PWT;
   // Stride-2 TMA mode: the patch is four boxes, one per (row parity, column parity) VIEW of the input (tensor maps with
   // pixel pitch 2 and row pitch 2: quarter-resolution images; zero fill outside = the conv's padding).  Inside a view
-  // the stride-2 walk of a tap is a unit-stride one, so every tap is a start-address shift in one of the four regions:
-  // tap (ky, kx) reads view ((ky+1)&1, (kx+1)&1) at box offset (ky>>1, kx>>1).  32-channel chunks = 64-byte pixel rows
-  // with the 64-byte swizzle.
-  constexpr bool S2TMA = TMA && MODE == S2K4;
+  // the stride-2 walk of a tap is a unit-stride one, so every tap is a start-address shift inside one view: tap (ky, kx)
+  // reads view ((ky+1)&1, (kx+1)&1) at box offset (ky>>1, kx>>1).  The TMA engine sustains about one box segment
+  // (one pixel of one view) per 6 cycles per SM: 32-channel chunks (64-byte segments) were measured segment-rate bound
+  // at 60 % of the tensor pipe, hence 64-channel chunks = 128-byte pixel rows with the 128-byte swizzle -- and, to keep
+  // the footprint at one chunk, a VIEW-granular ring: one stage = one parity view of one chunk (4 taps), the producer
+  // runs three views ahead of the MMAs.
   constexpr int VW = TILE_W * T + 1, VH = TILE_H + 1;                      // view box: 17 rows x (8T+1) pixels
-  constexpr int VREGION = ((VH * VW * 64 + 1023) / 1024) * 1024;
-  constexpr int A_STAGE = S2TMA ? 4 * VREGION : TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
-  constexpr int B_TAP = BN * G::CH * 2;    // one tap of one chunk: [k8][BN rows][16 B]
+  constexpr int VREGION = ((VH * VW * 128 + 1023) / 1024) * 1024;
+  constexpr int A_STAGE = S2TMA ? VREGION : TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
+  constexpr int B_TAP = BN * CHK * 2;      // one tap of one chunk: [k8][BN rows][16 B]
   constexpr int B_STAGE = GT * B_TAP;      // a weight stage carries GT taps
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
   float* sTab = reinterpret_cast<float*>(sB + BS * B_STAGE + ((sizeof(Bars) + 15) & ~15));  // [2 acc][A | B][BN] epilogue tables
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunks = p.Cin / G::CH;
+  const int nchunks = p.Cin / CHK;
   const int tiles_per_row = tiles_x * tiles_y;
   // whole filter fits the weight ring and every work item uses the same n-tile: load it once, never release it
   const bool b_resident = n_tiles == 1 && nchunks * (G::TAPS / GT) == BS;
@@ -290,22 +296,27 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       for (int w = w0; w < min(w0 + cw, num_work); ++w) {
           int n_tile, row, oy0, ox0;
           decode(w, n_tile, row, oy0, ox0);
+          if constexpr (S2TMA) {
+            for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v, ++ca) {  // v = row parity * 2 + column parity; odd views start one view pixel earlier
+                const int st = ca % AS;
+                mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
+                const uint32_t bar = smem_u32(&bars->a_full[st]);
+                mbar_expect_tx(bar, VH * VW * 128);
+                const uint64_t tmv = reinterpret_cast<uint64_t>(v == 0 ? &tmap : v == 1 ? &tmap2 : v == 2 ? &tmap3 : &tmap4);
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                    ::"r"(smem_u32(sA + st * A_STAGE)), "l"(tmv), "r"(c * CHK), "r"(ox0 - (v & 1)),
+                      "r"(oy0 - (v >> 1)), "r"(row), "r"(bar) : "memory");
+              }
+            }
+            continue;
+          }
           for (int c = 0; c < nchunks; ++c, ++ca) {
             const int st = ca % AS;
             mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
             const uint32_t bar = smem_u32(&bars->a_full[st]);
-            if constexpr (S2TMA) {
-              mbar_expect_tx(bar, 4 * VH * VW * 64);
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {  // v = row parity * 2 + column parity; odd views start one view pixel earlier
-                const uint64_t tmv = reinterpret_cast<uint64_t>(v == 0 ? &tmap : v == 1 ? &tmap2 : v == 2 ? &tmap3 : &tmap4);
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                    ::"r"(smem_u32(sA + st * A_STAGE + v * VREGION)), "l"(tmv), "r"(c * G::CH), "r"(ox0 - (v & 1)),
-                      "r"(oy0 - (v >> 1)), "r"(row), "r"(bar) : "memory");
-              }
-              continue;
-            }
             mbar_expect_tx(bar, PIXT * 128);
             // nch_split > 0: the K axis is the concatenation of two tensor views (chunks [0, nch_split) / the rest)
             const bool second = nch_split > 0 && c >= nch_split;
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
-      const uint32_t a_hi = S2TMA ? ((uint32_t)(((VW * 64) >> 4) & 0x3FFF) | (1u << 14) | (4u << 29))  // SWIZZLE_64B
+      const uint32_t a_hi = S2TMA ? ((uint32_t)(((VW * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))  // SWIZZLE_128B
                             : TMA ? ((uint32_t)(((PWT * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
                                   : ((uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14));
       const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
@@ -389,6 +400,34 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
         mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * T * BN;
+        if constexpr (S2TMA) {
+          // view-major tap order: view v = (py, px) holds taps ky = 1 - py + 2a, kx = 1 - px + 2b (a, b in {0, 1}) at box
+          // offset (a, b); the weight producer streams the taps in the same order
+          static_assert(!S2TMA || GT == 1, "stride-2 TMA path: one tap per weight stage");
+          for (int c = 0; c < nchunks; ++c) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              mbar_wait(bar_a_full + sa * 8, pa);
+              tc_fence_after();
+              const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (A_STAGE >> 4));
+#pragma unroll
+              for (int ab = 0; ab < 4; ++ab) {
+                mbar_wait(bar_b_full + sb * 8, pb);
+                tc_fence_after();
+                const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_STAGE >> 4));
+                const int a_off = ((ab >> 1) * VW + (ab & 1)) * 128;
+#pragma unroll
+                for (int tile = 0; tile < T; ++tile)
+                  umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_W * 128) >> 4), b_st, idesc,
+                                           (v | ab) ? 1u : (uint32_t)(c != 0), leader);
+                umma_commit_if(bar_b_empty + sb * 8, leader);
+                if (++sb == BS) { sb = 0; pb ^= 1; }
+              }
+              umma_commit_if(bar_a_empty + sa * 8, leader);
+              if (++sa == AS) { sa = 0; pa ^= 1; }
+            }
+          }
+        } else
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(bar_a_full + sa * 8, pa);
           tc_fence_after();
@@ -403,9 +442,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
 #pragma unroll
             for (int t = 0; t < GT; ++t) {
               const int tap = g * GT + t, ky = tap / G::KW, kx = tap - ky * G::KW;
-              const int a_off = S2TMA ? ((((ky + 1) & 1) * 2 + ((kx + 1) & 1)) * VREGION + ((ky >> 1) * VW + (kx >> 1)) * 64)
-                                : TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
-              constexpr int TILE_STEP = TILE_W * (S2TMA ? 64 : TMA ? 128 : 16);  // 8 pixels further along the patch row
+              const int a_off = TMA ? (ky * PWT + kx) * 128 : G::tap_offset(ky, kx, PLANE);
+              constexpr int TILE_STEP = TILE_W * (TMA ? 128 : 16);  // 8 pixels further along the patch row
 #pragma unroll
               for (int tile = 0; tile < T; ++tile)
                 umma_tap<KSTEPS, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * TILE_STEP) >> 4),
@@ -432,9 +470,14 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
         const int n_tile = w % n_tiles;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wblob) + (size_t)n_tile * per_tile * B_STAGE;
         for (int i = 0; i < per_tile; ++i) {
+          int j = i;
+          if constexpr (S2TMA) {  // view-major tap order of the MMA loop: (chunk, view (py, px), a, b) -> tap ky*4 + kx
+            const int c = i >> 4, v = (i >> 2) & 3, ab = i & 3;
+            j = c * 16 + (1 - (v >> 1) + 2 * (ab >> 1)) * 4 + (1 - (v & 1) + 2 * (ab & 1));
+          }
           mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
           mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_STAGE);
-          bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
+          bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)j * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
           if (++sb == BS) { sb = 0; pb ^= 1; }
         }
       }
@@ -495,8 +538,8 @@ template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1,
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
-template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };    // 152 KB views +  64 KB weights
-template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 8; };   // 152 KB views +  64 KB weights
+template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 1, A = 4, B = 8; };    // 148 KB (4 view stages) + 64 KB weights
+template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };   // 148 KB (4 view stages) + 64 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
 static int make_patch_tmap(const ConvParams& p, const __nv_bfloat16* src, int C, int pw, int ph, CUtensorMap* out) {
@@ -519,9 +562,10 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   using St = Stages<MODE, BN, TMA, V>;
   constexpr int AS = St::A, BS = St::B, T = St::T, GT = St::GT;
   using G = Geo<MODE, TMA ? 1 : T>;
-  constexpr int a_stage = (TMA && MODE == S2K4) ? 4 * ((((TILE_H + 1) * (TILE_W * T + 1) * 64 + 1023) / 1024) * 1024)
+  constexpr int CHK = (TMA && MODE == S2K4) ? 64 : G::CH;
+  constexpr int a_stage = (TMA && MODE == S2K4) ? ((((TILE_H + 1) * (TILE_W * T + 1) * 128 + 1023) / 1024) * 1024)
                           : TMA ? (((TILE_W * T + G::HALO) * G::PH * 128 + 1023) / 1024) * 1024 : Sizes<MODE, T>::A_STAGE;
-  constexpr int smem = AS * a_stage + BS * GT * BN * G::CH * 2 + (((int)sizeof(Barriers<AS, BS>) + 15) & ~15) + 4 * BN * 4 + 64;
+  constexpr int smem = AS * a_stage + BS * GT * BN * CHK * 2 + (((int)sizeof(Barriers<AS, BS>) + 15) & ~15) + 4 * BN * 4 + 64;
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static_assert(2 * T * BN <= 512, "TMEM budget exceeded");
   static int num_sms = 0;
@@ -551,6 +595,13 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
                                                                                 (int)work, tmap, tmap2, tmap3, tmap4, nch_split);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
+}
+
+// channels per chunk of the stride-2 weight tiles: 64 for the TMA path, 32 for the cp.async gather (DYF_UMMA_A=cpasync);
+// process-wide, so that finalize (re-packing) and launch agree
+int s2k4_weights_chunk() {
+  static const char* env_a = getenv("DYF_UMMA_A");
+  return (env_a && env_a[0] == 'c') ? 32 : 64;
 }
 
 int mode_of(int k, int stride, int pad) {
@@ -645,7 +696,12 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     }
     return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
   }
-  if (want_tma && !((p.Hi | p.Wi) & 1)) {  // four parity views of the input, 64-byte swizzle
+  // The stride-2 weight tiles were packed (finalize) for 64-channel chunks iff Cin % 64 == 0 and the TMA path is on: those
+  // layers MUST take the TMA kernel -- when it cannot run (odd input size, no tensor map) the layer is handed back to the
+  // mma.sync pipeline rather than to the 32-channel gather kernel.
+  const bool w64 = p.Cin % 64 == 0 && s2k4_weights_chunk() == 64;
+  if (w64 && !(want_tma && !((p.Hi | p.Wi) & 1))) return 0;
+  if (w64) {  // four parity views of the input
     constexpr int T2 = Stages<S2K4, 128, true>::T;
     using Key = std::tuple<const void*, int, int, int, int>;
     struct Quad { CUtensorMap m[4]; };
@@ -657,15 +713,16 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
       Quad q;
       const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Wi / 2, (cuuint64_t)p.Hi / 2, (cuuint64_t)p.rows};
       const cuuint64_t strides[3] = {(cuuint64_t)4 * p.Cin, (cuuint64_t)4 * p.Wi * p.Cin, (cuuint64_t)2 * p.Hi * p.Wi * p.Cin};
-      const cuuint32_t box[4] = {32, TILE_W * T2 + 1, TILE_H + 1, 1};
+      const cuuint32_t box[4] = {64, TILE_W * T2 + 1, TILE_H + 1, 1};
       for (int v = 0; v < 4 && ok; ++v)
-        ok = make_tmap4(p.in + ((size_t)(v >> 1) * p.Wi + (v & 1)) * p.Cin, dims, strides, box, &q.m[v], CU_TENSOR_MAP_SWIZZLE_64B) == 0;
+        ok = make_tmap4(p.in + ((size_t)(v >> 1) * p.Wi + (v & 1)) * p.Cin, dims, strides, box, &q.m[v]) == 0;
       if (ok) {
         if (cache.size() > 1024) cache.clear();
         it = cache.emplace(key, q).first;
       }
     }
-    if (ok) return n64 ? launch_t<64, S2K4, true>(p, stream, it->second.m) : launch_t<128, S2K4, true>(p, stream, it->second.m);
+    if (!ok) return 0;
+    return n64 ? launch_t<64, S2K4, true>(p, stream, it->second.m) : launch_t<128, S2K4, true>(p, stream, it->second.m);
   }
   return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
 }
@@ -674,7 +731,7 @@ int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, 
                        cudaStream_t s) {
   const int mode = mode_of(k, stride, pad);
   if (mode < 0) { set_error("repack_umma: unsupported geometry"); return -1; }
-  const int taps = k * k, ch = mode == S2K4 ? 32 : 64;
+  const int taps = k * k, ch = mode == S2K4 ? ((I % 64 == 0) ? s2k4_weights_chunk() : 32) : 64;
   const long long total = (long long)umma_padded_cout(O) * I * taps;
   repack_umma_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, O, I, umma_tile_n(O), taps, ch, standardize);
   DYF_LAUNCH_OK("repack_umma_kernel");
