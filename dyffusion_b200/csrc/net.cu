@@ -253,7 +253,8 @@ int Net::build_unet_simple() {
     // 3x3 decoder blocks on large grids run as ONE kernel: upsample + concat + conv as a composite conv on the low-res
     // grid (conv_up.cu).  Small grids keep the two-kernel path (their border tiles would dominate).
     const char* env_min = getenv("DYF_UPFUSE_MIN");  // smallest upsampled grid side that takes the fused kernel
-    const int fuse_min = env_min ? atoi(env_min) : 128;  // measured: below 128 the border phases + wave quantisation eat the gain
+    const int fuse_min = env_min ? atoi(env_min) : 64;  // measured on the NS step: 64 beats 128 by 2 %; at 32 (one super-tile per
+                                                        // image) the border phases + wave quantisation eat the gain
     const bool fuse_up = dec_k[i] == 3 && std::min(H, W) >= fuse_min && conv_up_shape_ok(c0, c1, dec_out[i], H / 2, W / 2) &&
                          !getenv("DYF_DISABLE_UPFUSE");
     int up = BUF_NONE;
