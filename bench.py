@@ -8,6 +8,13 @@
 
 A "step" is one `sample()` call over one batch of synthetic Navier-Stokes rows: 16 forecaster + 44 interpolator
 UNet forwards (cold sampling + refinement, interpolator dropout on).  Prints ONE JSON line on rank 0.
+
+Timed region: K calls of `sample()` with device-resident inputs, one CUDA-event pair around the whole region (max over
+ranks), barrier + synchronize on both sides; inside it only the launches of the dominant kernel class carry their own
+event pairs (`roofline`: algorithmic FLOPs / measured device time of that kernel, live).  Before it: W >= 3 warm-up steps
+and one extra untimed step with events around EVERY launch (`kernel_ms_per_step`).  After it: the same K steps end to end
+through `predict_forward` with pinned host buffers (`e2e`), then (N=1) the CPU baseline.  The working set of one network
+forward (>= 5 GB of activations) is far beyond the 126 MB L2, so no explicit flush is needed between steps.
 """
 from __future__ import annotations
 
