@@ -236,14 +236,18 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(const AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------- full attention
-// One block per (head, row): K^T and V of the head live in shared memory (n <= 1024 positions), each warp walks over
-// query positions: scores (lane = key position), softmax, dropout on the probabilities, then P.V (lane = channel).
+// One block per (head, row): K^T and V of the head live in shared memory (n <= 1024 positions).  Each warp handles FOUR
+// queries at a time, so that every shared-memory read of K^T / V feeds four FMAs: scores (lane = key position; the four
+// scaled queries are read as one broadcast float4 per channel), softmax, dropout on the probabilities, then P.V (lane =
+// channel; the four probabilities of a key are one broadcast float4).
+constexpr int AQ = 4;  // queries per warp pass
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
-  extern __shared__ float s_mem[];
+  extern __shared__ __align__(16) float s_mem[];
   const int n = p.n, np = n | 1;
-  float* s_kt = s_mem;            // [DH][np]
-  float* s_v = s_mem + DH * np;   // [n][DH]
-  float* s_p = s_v + n * DH;      // [8 warps][n]
+  float* s_kt = s_mem;                       // [DH][np]
+  float* s_v = s_mem + DH * np;              // [n][DH]
+  float* s_p = s_v + n * DH;                 // [8 warps][n][AQ]   (scores, then probabilities)
+  float* s_q = s_p + 8 * n * AQ;             // [8 warps][DH][AQ]  (scaled queries)
   const int h = blockIdx.x, r = blockIdx.y;
   const int ld = 3 * p.heads * DH;
   const __nv_bfloat16* base = p.qkv + (size_t)r * n * ld + h * DH;
@@ -255,36 +259,58 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float scale = rsqrtf((float)DH);
-  float* pw = s_p + warp * n;
-  for (int i = warp; i < n; i += 8) {
-    const float q = __bfloat162float(base[(size_t)i * ld + lane]) * scale;  // lane = d
-    float qv[DH];  // every lane needs the whole query vector: broadcast it once (all lanes participate)
+  float4* pw = reinterpret_cast<float4*>(s_p + (size_t)warp * n * AQ);
+  float4* qw = reinterpret_cast<float4*>(s_q + (size_t)warp * DH * AQ);
+  for (int i0 = warp * AQ; i0 < n; i0 += 8 * AQ) {
+    {  // the four queries, lane = channel
+      float q[AQ];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) qv[d] = __shfl_sync(0xffffffffu, q, d);
-    float mx = -INFINITY;
-    for (int j = lane; j < n; j += 32) {  // lane = key position
-      float sc = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) sc = fmaf(qv[d], s_kt[d * np + j], sc);
-      pw[j] = sc;
-      mx = fmaxf(mx, sc);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < n; j += 32) {
-      const float e = __expf(pw[j] - mx);
-      pw[j] = e;
-      sum += e;
-    }
-    const float inv = 1.f / warp_sum(sum);
-    if (p.drop.thresh) {
-      const uint64_t e0 = (((uint64_t)r * p.heads + h) * n + i) * n;
-      for (int j = lane; j < n; j += 32) pw[j] = keep1(p.drop, e0 + j) ? pw[j] * p.drop.scale : 0.f;
+      for (int t = 0; t < AQ; ++t) q[t] = i0 + t < n ? __bfloat162float(base[(size_t)(i0 + t) * ld + lane]) * scale : 0.f;
+      qw[lane] = make_float4(q[0], q[1], q[2], q[3]);
     }
     __syncwarp();
-    float o = 0.f;  // lane = d
-    for (int j = 0; j < n; ++j) o = fmaf(pw[j], s_v[j * DH + lane], o);
-    p.out[((size_t)r * n + i) * (p.heads * DH) + h * DH + lane] = __float2bfloat16_rn(o * inv);
+    float mx[AQ] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int j = lane; j < n; j += 32) {  // lane = key position
+      float sc[AQ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int d = 0; d < DH; ++d) {
+        const float k = s_kt[d * np + j];
+        const float4 q = qw[d];
+        sc[0] = fmaf(q.x, k, sc[0]); sc[1] = fmaf(q.y, k, sc[1]); sc[2] = fmaf(q.z, k, sc[2]); sc[3] = fmaf(q.w, k, sc[3]);
+      }
+      pw[j] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+#pragma unroll
+      for (int t = 0; t < AQ; ++t) mx[t] = fmaxf(mx[t], sc[t]);
+    }
+    float sum[AQ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < AQ; ++t) mx[t] = warp_max(mx[t]);
+    for (int j = lane; j < n; j += 32) {
+      float4 e = pw[j];
+      e.x = __expf(e.x - mx[0]); e.y = __expf(e.y - mx[1]); e.z = __expf(e.z - mx[2]); e.w = __expf(e.w - mx[3]);
+      sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+      if (p.drop.thresh) {  // dropout on the probabilities (attention.py:59,70); element = ((row, head, query), key)
+        const uint64_t e0 = (((uint64_t)r * p.heads + h) * n + i0) * n + j;
+        e.x = keep1(p.drop, e0) ? e.x * p.drop.scale : 0.f;
+        e.y = keep1(p.drop, e0 + n) ? e.y * p.drop.scale : 0.f;
+        e.z = keep1(p.drop, e0 + 2 * (uint64_t)n) ? e.z * p.drop.scale : 0.f;
+        e.w = keep1(p.drop, e0 + 3 * (uint64_t)n) ? e.w * p.drop.scale : 0.f;
+      }
+      pw[j] = e;
+    }
+    float inv[AQ];
+#pragma unroll
+    for (int t = 0; t < AQ; ++t) inv[t] = 1.f / warp_sum(sum[t]);
+    __syncwarp();
+    float o[AQ] = {0.f, 0.f, 0.f, 0.f};  // lane = channel
+    for (int j = 0; j < n; ++j) {
+      const float v = s_v[j * DH + lane];
+      const float4 pr = pw[j];
+      o[0] = fmaf(pr.x, v, o[0]); o[1] = fmaf(pr.y, v, o[1]); o[2] = fmaf(pr.z, v, o[2]); o[3] = fmaf(pr.w, v, o[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < AQ; ++t)
+      if (i0 + t < n) p.out[((size_t)r * n + i0 + t) * (p.heads * DH) + h * DH + lane] = __float2bfloat16_rn(o[t] * inv[t]);
     __syncwarp();
   }
 }
@@ -316,12 +342,12 @@ int launch_linear_attention(const AttnParams& p, cudaStream_t s) {
 }
 
 int launch_attention(const AttnParams& p, cudaStream_t s) {
-  if (p.n > 1024) {
-    set_error("full attention is built for bottleneck grids (n <= 1024 positions); keep_spatial_dims on large grids "
-              "needs the streaming-softmax variant");
+  if (p.n > 576) {
+    set_error("full attention is built for bottleneck grids (n <= 576 positions = 24 x 24, K/V/P resident in shared memory); "
+              "keep_spatial_dims on large grids needs the streaming-softmax variant");
     return -4;
   }
-  const size_t smem = ((size_t)DH * (p.n | 1) + (size_t)p.n * DH + 8 * (size_t)p.n) * sizeof(float);
+  const size_t smem = ((size_t)DH * (p.n | 1) + (size_t)p.n * DH + 8 * (size_t)p.n * AQ + 8 * DH * AQ) * sizeof(float) + 16;
   static size_t configured = 0;
   if (smem > configured) {
     DYF_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
