@@ -308,11 +308,19 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormPar
   s_part[threadIdx.x][0] = s1;
   s_part[threadIdx.x][1] = s2;
   __syncthreads();
-  if (threadIdx.x < p.G) {  // thread g sums the partials of group g in thread order
-    const int g = threadIdx.x;
+  // tree over the pixel lanes of every channel chunk (thread = (pixel lane, chunk), pstep = 256 / chunks is a power of two),
+  // then thread g adds the chunks of group g in index order: a fixed order, so the statistics are bit-reproducible
+  for (int half = pstep >> 1; half > 0; half >>= 1) {
+    if ((int)threadIdx.x < half * chunks) {
+      s_part[threadIdx.x][0] += s_part[threadIdx.x + half * chunks][0];
+      s_part[threadIdx.x][1] += s_part[threadIdx.x + half * chunks][1];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < p.G) {
+    const int g = threadIdx.x, cpc = cpg >> 3;  // chunks per group
     float a = 0.f, b = 0.f;
-    for (int t = 0; t < (int)blockDim.x; ++t)
-      if (((t % chunks) << 3) / cpg == g) { a += s_part[t][0]; b += s_part[t][1]; }
+    for (int c = g * cpc; c < (g + 1) * cpc; ++c) { a += s_part[c][0]; b += s_part[c][1]; }
     float* o = p.stats + (((size_t)r * p.G + g) * GN_SLABS + blockIdx.x) * 2;
     o[0] = a;
     o[1] = b;
