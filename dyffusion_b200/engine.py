@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdyffusion_b200.so")
+LIB_PATH = os.environ.get("DYF_LIB") or os.path.join(_HERE, "libdyffusion_b200.so")  # DYF_LIB: A/B builds of the same ABI
 
 ARCH_UNET_SIMPLE, ARCH_UNET_RESNET, ARCH_CONVNET = 0, 1, 2
 
