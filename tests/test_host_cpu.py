@@ -61,6 +61,29 @@ def test_no_cpu_fallback():
         m(x, time=torch.zeros(1), condition=torch.zeros(1, 5, 10, 10))
 
 
+def test_no_cpu_fallback_for_the_widening_rows():
+    """Ensemble metrics and boundary conditions: CPU tensors are refused, and the C entry points themselves fail with
+    DYF_ERR_CUDA when there is no device (no host arithmetic anywhere behind the ABI)."""
+    import ctypes as C
+
+    import dyffusion_b200.engine as E
+    from dyffusion_b200.boundary import boundary_conditions
+    from dyffusion_b200.metrics import evaluate_ensemble_prediction
+
+    with pytest.raises(E.EngineError):
+        evaluate_ensemble_prediction(torch.zeros(3, 2, 4, 5, 5), torch.zeros(2, 4, 5, 5))
+    with pytest.raises(E.EngineError):
+        boundary_conditions("spring-mesh", torch.zeros(2, 4, 10, 10), torch.zeros(2, 4, 10, 10), {})
+    if not torch.cuda.is_available():
+        buf = (C.c_double * 8)()
+        fbuf = (C.c_float * 64)()
+        ws = (C.c_char * 4096)()
+        rc = E.LIB.dyf_ensemble_metrics(C.addressof(fbuf), C.addressof(fbuf), 2, 1, 4, C.addressof(buf), None, C.addressof(ws), 4096, None)
+        assert rc == -2 and b"no CPU fallback" in E.LIB.dyf_last_error()
+        rc = E.LIB.dyf_boundary_conditions_spring_mesh(C.addressof(fbuf), C.addressof(ws), C.addressof(fbuf), 1, 1, 2, 2, None)
+        assert rc == -2 and b"no CPU fallback" in E.LIB.dyf_last_error()
+
+
 def test_product_never_imports_oracle():
     bad = []
     for dirpath, _, files in os.walk(os.path.join(ROOT, "dyffusion_b200")):
