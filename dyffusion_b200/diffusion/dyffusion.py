@@ -108,9 +108,11 @@ class DYffusion(BaseModel):
         if isinstance(interpolator, EngineBackbone):
             interpolator = InterpolatorHandle(interpolator, horizon=timesteps)
         if interpolator_local_checkpoint_path is not None:
-            state = torch.load(interpolator_local_checkpoint_path, map_location="cpu")
+            from ..checkpoint import split_state_dict  # Lightning .ckpt of the interpolator's own run, or a bare state dict
+            state = torch.load(interpolator_local_checkpoint_path, map_location="cpu", weights_only=False)
             state = state.get("state_dict", state)
-            state = {k[len("model."):] if k.startswith("model.") else k: v for k, v in state.items()}
+            if any(k.startswith("model.") for k in state):
+                state = split_state_dict(state)["model"]
             interpolator.model.load_state_dict(state)
         self.interpolator = _freeze(interpolator)
         self.interpolator_window = self.interpolator.window
