@@ -18,18 +18,29 @@ def boundary_conditions(physical_system: str, preds: torch.Tensor, targets: torc
         raise ValueError("preds must be a contiguous float32 tensor (it is updated in place)")
     dev = preds.device
     if physical_system == "navier-stokes":
-        if preds.ndim != 4 or preds.shape[0] != batch_size:
-            raise ValueError("navier-stokes boundary conditions expect preds of shape (batch, 3, H, W)")
-        b, c, h, w = preds.shape
+        if preds.ndim < 4:
+            raise ValueError("navier-stokes boundary conditions expect preds of shape (*, 3, H, W)")
+        c, h, w = preds.shape[-3:]
         mask = metadata["fixed_mask"].to(dev)
         assert tuple(mask.shape[1:]) == (c, h, w), f"fixed_mask={tuple(mask.shape[1:])}, predictions={tuple(preds.shape)}"
-        mask = mask.to(torch.uint8).contiguous()
-        vy = metadata["vertices"][:, 1, 0, :].to(dev, torch.float32).contiguous()
-        vel = metadata["in_velocity"].reshape(batch_size).to(dev, torch.float32).contiguous()
+        if preds.shape[0] < batch_size:  # the reference's `preds[b_i, ...]` for b_i >= preds.shape[0]
+            raise IndexError(f"index {preds.shape[0]} is out of bounds for dimension 0 with size {preds.shape[0]}")
+        # The reference indexes the LEADING axis of `preds` with the sample index (`preds[b_i, ..., mask_b_i] = 0`, :268-276):
+        # for (batch, 3, H, W) that is the sample itself; for ensemble predictions (members, batch, 3, H, W) it is member
+        # b_i, written for every sample with sample b_i's mask / inflow.  Reproduced as is: slice [0, batch) of the leading
+        # axis, `inner` trailing rows per slice sharing the metadata of the slice index.
+        inner = 1
+        for d in preds.shape[1:-3]:
+            inner *= int(d)
+        rep = (lambda t: t) if inner == 1 else (lambda t: t.repeat_interleave(inner, dim=0))
+        mask = rep(mask.to(torch.uint8)).contiguous()
+        vy = rep(metadata["vertices"][:, 1, 0, :].to(dev, torch.float32)).contiguous()
+        vel = rep(metadata["in_velocity"].reshape(batch_size).to(dev, torch.float32)).contiguous()
         per_sample = not isinstance(time, float)
-        t = (time.reshape(batch_size) if per_sample else torch.tensor([time])).to(dev, torch.float32).contiguous()
+        t = (rep(time.reshape(batch_size)) if per_sample else torch.tensor([time])).to(dev, torch.float32).contiguous()
         E._check(E.LIB.dyf_boundary_conditions_navier_stokes(preds.data_ptr(), mask.data_ptr(), vy.data_ptr(), vel.data_ptr(),
-                                                           t.data_ptr(), int(per_sample), b, c, h, w, E._stream_ptr()))
+                                                           t.data_ptr(), int(per_sample), batch_size * inner, c, h, w,
+                                                           E._stream_ptr()))
     elif physical_system == "spring-mesh":
         mask = metadata["fixed_mask"].to(dev)
         assert mask.shape[1] == 4, f"fixed_mask_pq={tuple(mask.shape[1:])}, should be (4, 10, 10)"

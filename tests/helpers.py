@@ -86,3 +86,46 @@ def sampler_case_inputs(name, dataset, rows):
 def oracle_schedule(dk):
     return O.Schedule(dk["timesteps"], dk["schedule"], dk["additional_interpolation_steps"],
                       dk["additional_interpolation_steps_factor"], dk["interpolate_before_t1"], dk["sampling_schedule"])
+
+
+# ---------------------------------------------------------------- autoregressive rollout cases
+ROLLOUT_CASES = {
+    # name: dataset, horizon, ensemble members, batch, autoregressive steps, physical system of the boundary conditions
+    "rollout_spring": dict(dataset="spring", horizon=4, members=3, batch=2, ar_steps=2, system="spring-mesh"),
+    "rollout_ns": dict(dataset="ns", horizon=2, members=2, batch=2, ar_steps=1, system="navier-stokes"),
+    "rollout_spring_single": dict(dataset="spring", horizon=3, members=1, batch=3, ar_steps=1, system="spring-mesh"),
+}
+
+
+def rollout_case(name):
+    """Synthetic evaluation batch of the reference's layout (`dynamics` (B, T, C, H, W), `condition`, `metadata`) and the
+    `t0` / `dt` the datamodule would hand over (physical_systems_benchmark.py:299-303)."""
+    c = ROLLOUT_CASES[name]
+    d = C.DATASETS[c["dataset"]]
+    (Hh, Ww), ch, b = d["spatial"], d["channels"], c["batch"]
+    T = 1 + c["horizon"] * (c["ar_steps"] + 1)
+    batch = {"dynamics": synth_tensor(f"{name}.dyn", (b, T, ch, Hh, Ww)),
+             "condition": synth_tensor(f"{name}.static", (b, d["static"], Hh, Ww), kind="mask")}
+    fixed = synth_tensor(f"{name}.fixed", (b, ch, Hh, Ww), kind="mask") > 0
+    if c["system"] == "spring-mesh":
+        batch["metadata"] = {"fixed_mask": fixed, "features": synth_tensor(f"{name}.features", (b, 5, ch, Hh, Ww))}
+        t0, dt = 0.0, 1.0
+    else:
+        batch["metadata"] = {"fixed_mask": fixed, "vertices": synth_tensor(f"{name}.vert", (b, 2, Hh, Ww)).abs() * 0.2,
+                             "in_velocity": 0.5 + synth_tensor(f"{name}.vel", (b, 1)).abs()}
+        t0, dt = synth_tensor(f"{name}.t0", (b,)).abs(), torch.full((b,), 0.05)
+    return c, batch, t0, dt
+
+
+def oracle_rollout_sampler(dataset, horizon, seeds=(3, 2)):
+    """`sample(ic, static)` over the oracle sampler with the synthetic weights of tests/golden (forecaster seed 3,
+    interpolator seed 2), interpolator dropout off."""
+    shapes = golden_json("state_shapes.json")
+    sdF = synth_state_dict({k: tuple(v) for k, v in shapes[f"{dataset}_F"].items()}, seed=seeds[0])
+    sdI = synth_state_dict({k: tuple(v) for k, v in shapes[f"{dataset}_I"].items()}, seed=seeds[1])
+    dk = C.diffusion_kwargs(dataset, horizon=horizon)
+    F, I, sched = oracle_net(dataset, "F", sdF), oracle_net(dataset, "I", sdI), oracle_schedule(dk)
+    return lambda ic, static: O.sample_loop(
+        F, I, sched, ic, static, num_input_channels=C.DATASETS[dataset]["channels"],
+        forward_conditioning=dk["forward_conditioning"],
+        refine_intermediate_predictions=dk["refine_intermediate_predictions"])

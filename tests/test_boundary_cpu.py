@@ -19,6 +19,12 @@ def _ns_case(b=3, seed=0):
     return preds, torch.zeros(b, 3, 221, 42), meta
 
 
+def _ns_ensemble_case(members=3, b=2, seed=9):
+    """(members, batch, 3, H, W) predictions, as the rollout hands them over (forecasting_multi_horizon.py:175-182)."""
+    _, tg, meta = _ns_case(b=b, seed=seed)
+    return torch.randn(members, b, 3, 221, 42, generator=torch.Generator().manual_seed(1)), tg, meta
+
+
 def _spring_case(b=4, lead=None, seed=1):
     g = torch.Generator().manual_seed(seed)
     shape = (b, 4, 10, 10) if lead is None else (lead, b, 4, 10, 10)
@@ -55,6 +61,7 @@ def test_oracle_equals_reference_method():
     from src.datamodules.physical_systems_benchmark import PhysicalSystemsBenchmarkDataModule as DM
     for system, case, kw in (("navier-stokes", _ns_case(), dict(time=1.3)),
                              ("navier-stokes", _ns_case(seed=5), dict(time=torch.tensor([0.1, 0.5, 2.0]))),
+                             ("navier-stokes", _ns_ensemble_case(), dict(time=torch.tensor([0.3, 1.1]))),
                              ("spring-mesh", _spring_case(), {}), ("spring-mesh", _spring_case(lead=5), {})):
         preds, tg, meta = case
         fake = types.SimpleNamespace(hparams=types.SimpleNamespace(physical_system=system))
