@@ -78,6 +78,7 @@ def _load() -> C.CDLL:
         "dyf_ensemble_metrics": (C.c_int, [vp, vp, i32, C.c_int64, C.c_int64, vp, vp, vp, sz, vp]),
         "dyf_boundary_conditions_navier_stokes": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dyf_boundary_conditions_spring_mesh": (C.c_int, [vp, vp, vp, C.c_int64, i32, i32, i32, vp]),
+        "dyf_window_gather": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), i32, i32, vp, vp]),
         "dyf_profile_enable": (C.c_int, [i32]),
         "dyf_profile_filter": (C.c_int, [i32]),
         "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -98,7 +99,7 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
             "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read",
             "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics", "dyf_boundary_conditions_navier_stokes",
-            "dyf_boundary_conditions_spring_mesh"]
+            "dyf_boundary_conditions_spring_mesh", "dyf_window_gather"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
                   "attention", "conv_up"]
 

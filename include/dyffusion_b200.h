@@ -198,6 +198,19 @@ int dyf_boundary_conditions_navier_stokes(float* preds, const uint8_t* fixed_mas
 int dyf_boundary_conditions_spring_mesh(float* preds, const uint8_t* fixed_mask, const float* base_q, int64_t lead, int32_t batch,
                                         int32_t height, int32_t width, void* stream);
 
+/* Widening row SURVEY.md 8f-4 (second half) -- GPU-resident sliding-window dataset.
+ * Replaces: the example tensor that `PhysicalSystemsBenchmarkDataModule.create_dataset_multi_horizon` materialises on the host
+ * (src/datamodules/physical_systems_benchmark.py:191-243: `sliding_window_view` over every trajectory, re-arranged to
+ * (example, window + horizon, C, H, W) and concatenated) together with the DataLoader collation / host->device copy of each
+ * batch.  The trajectories stay in HBM once, back to back; an example is `frames_per_example` consecutive frames.
+ * frames: [n_frames, frame_elems] fp32 (device); first_frame_host: HOST array of `batch` start frames (trajectory base +
+ * example offset; it travels as a kernel parameter); out: [batch, frames_per_example, frame_elems] fp32 (device).
+ * A window reaching outside [0, n_frames) is DYF_ERR_ARG (keeping windows inside ONE trajectory is the caller's index
+ * arithmetic, dyffusion_b200/datasets.py).  Also used with frames_per_example = 1 to gather per-trajectory tensors
+ * (the static `condition`, masks) by trajectory index. */
+int dyf_window_gather(const float* frames, int64_t n_frames, int64_t frame_elems, const int64_t* first_frame_host, int32_t batch,
+                      int32_t frames_per_example, float* out, void* stream);
+
 /* Test hook: writes the keep-mask (1/0 bytes) the engine's dropout draws for a tensor of `n_elems` elements
  * (NHWC element order, channel count `channels`) at (seed, stream, site, p).  Lets tests replay engine masks in
  * the oracle. */

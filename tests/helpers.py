@@ -129,3 +129,24 @@ def oracle_rollout_sampler(dataset, horizon, seeds=(3, 2)):
         F, I, sched, ic, static, num_input_channels=C.DATASETS[dataset]["channels"],
         forward_conditioning=dk["forward_conditioning"],
         refine_intermediate_predictions=dk["refine_intermediate_predictions"])
+
+
+# ---------------------------------------------------------------- trajectory store cases
+def synth_trajectories(system, lengths, seed=0):
+    """Objects shaped like `TrajectoryDataset.__getitem__`'s result (datasets/physical_systems_benchmark.py:66-160)."""
+    import types
+    ch, hw, st = (3, (221, 42), 2) if system == "navier-stokes" else (4, (10, 10), 1)
+    out = []
+    for i, T in enumerate(lengths):
+        tag = f"traj.{system}.{i}"
+        meta = {"name": f"traj_{i:05d}", "num_time_steps": T, "time_step_size": 0.05 * (1 + i % 2)}
+        tr = types.SimpleNamespace(
+            features=synth_tensor(f"{tag}.features", (T, ch, *hw), seed).numpy(),
+            condition=synth_tensor(f"{tag}.cond", (st, *hw), seed, kind="mask").numpy(),
+            fixed_mask=(synth_tensor(f"{tag}.fixed", (ch, *hw), seed, kind="mask") > 0).numpy(),
+            t=(0.1 * i + meta["time_step_size"] * torch.arange(T, dtype=torch.float32)).numpy(), trajectory_meta=meta, vertices=[])
+        if system == "navier-stokes":
+            meta["in_velocity"] = 0.5 + 0.25 * i
+            tr.vertices = (synth_tensor(f"{tag}.vert", (2, *hw), seed).abs() * 0.2).numpy()
+        out.append(tr)
+    return out
