@@ -147,8 +147,9 @@ class TrajectoryWindows:
         idx = torch.tensor(trajs, dtype=torch.long, device=self.device)
         for key, v in self._scalars.items():
             meta[key] = v.index_select(0, idx)
-        if self.t is not None and len({int(self.t[i].numel()) for i in set(trajs)}) == 1:
-            meta["t"] = torch.stack([self.t[i] for i in trajs]).to(self.device)
+        if self.t is not None:  # (B, T) like the reference's collate; trajectories of unequal length (which the reference
+            same = len({int(self.t[i].numel()) for i in set(trajs)}) == 1  # cannot collate) keep the column that is read: t[:, :1]
+            meta["t"] = torch.stack([self.t[i] if same else self.t[i][:1] for i in trajs]).to(self.device)
         batch["metadata"] = meta
         return batch
 

@@ -51,10 +51,10 @@ def test_batches_equal_the_reference_examples(system, lengths, window, horizon):
 def test_many_examples_per_launch_and_errors():
     from dyffusion_b200.datasets import TrajectoryWindows, window_gather
     import dyffusion_b200.engine as E
-    trajs = H.synth_trajectories("spring-mesh", [200, 150])
+    trajs = H.synth_trajectories("spring-mesh", [300, 250])
     want = dataset_oracle.create_dataset_multi_horizon(trajs, 1, 5)
     ds = TrajectoryWindows(trajs, 1, 5, "spring-mesh")
-    idx = list(range(len(ds)))[::-1]  # 338 examples: three launches of <= 128 table entries
+    idx = list(range(len(ds)))[::-1]  # 540 examples: two launches (448 table entries per launch)
     assert np.array_equal(ds.get_batch(idx)["dynamics"].cpu().numpy(), want["dynamics"][idx])
     odd = torch.arange(7 * 3 * 5, dtype=torch.float32).reshape(7, 3, 5).cuda()  # 15-float frames: 4-byte path
     assert torch.equal(window_gather(odd, [4, 0, 2], 3), torch.stack([odd[4:7], odd[0:3], odd[2:5]]))

@@ -3,10 +3,10 @@ around the engine's DYffusion drop-in (native sampler) with the on-device bounda
 (a) the reference's own `_evaluation_step` run in the build container (tests/golden/rollout_*.pt) and
 (b) the oracle rollout (oracle sampler + oracle boundary conditions) on the same synthetic batch.
 
-Stated tolerance: rel-L2 <= 5e-2 per horizon within the first sampler call (the per-trajectory bound of
-tests/test_gpu_parity.py: bf16 operands and activations), <= 1.5e-1 after autoregressive hand-offs (each hand-off feeds the
-previous call's error back in as the initial condition; the synthetic weights amplify ~3x per call).  The boundary values
-themselves are masked writes: exact."""
+Stated tolerance: rel-L2 <= 5e-2 per horizon (the per-trajectory bound of tests/test_gpu_parity.py: bf16 operands and
+activations), also after the autoregressive hand-offs, each of which feeds the previous call's error back in as the initial
+condition.  Measured on B200: <= 1.6e-2 over 3 chained spring-mesh calls, <= 6.8e-3 over 2 chained Navier-Stokes calls
+(profiles/r01_widening.md).  The boundary values themselves are masked writes: exact."""
 import functools
 
 import numpy as np
@@ -55,7 +55,7 @@ def test_rollout_vs_reference_golden(name):
         assert torch.equal(out[f"t{t}_targets"].cpu(), batch["dynamics"][:, t])
         e = H.rel_l2(got.cpu(), want)
         errs.append(e)
-        assert e <= (5e-2 if t <= c["horizon"] else 1.5e-1), (name, t, errs)
+        assert e <= 5e-2, (name, t, errs)
     print(name, "rel-L2 per horizon:", " ".join(f"{e:.2e}" for e in errs))
     fm = batch["metadata"]["fixed_mask"]
     last = out[f"t{T}_preds"].cpu()
@@ -82,7 +82,7 @@ def test_rollout_vs_oracle_and_test_step_metrics(name):
     T = c["horizon"] * (c["ar_steps"] + 1)
     for t in range(1, T + 1):
         e = H.rel_l2(out[f"t{t}_preds"].cpu(), torch.from_numpy(want[f"t{t}_preds"]))
-        assert e <= (5e-2 if t <= c["horizon"] else 1.5e-1), (name, t, e)
+        assert e <= 5e-2, (name, t, e)
     # a second evaluation is bit-identical (dropout off; no atomics anywhere on the path)
     again = ro.evaluation_step(dbatch, "test", boundary_conditions=bc, t0=t0, dt=dt)
     assert all(torch.equal(out[k], again[k]) for k in out)
@@ -91,8 +91,10 @@ def test_rollout_vs_oracle_and_test_step_metrics(name):
         p, tg = ro.stack_trajectory(out)
         assert tuple(p.shape) == (c["members"], T, c["batch"], *batch["dynamics"].shape[2:])
         ref = metrics_oracle.evaluate_ensemble_prediction(p.cpu().numpy(), tg.cpu().numpy(), mean_over_samples=False)
-        for k in ("crps", "mse", "ssr"):
+        for k in ("crps", "mse"):
             assert np.allclose(got[k], ref[k], rtol=2e-5), k
+        # dropout off and no input noise: the members coincide, the spread is 0 up to fp32 rounding of the variance
+        assert np.allclose(got["ssr"], ref["ssr"], rtol=2e-5, atol=1e-6)
 
 
 def test_navier_stokes_boundary_conditions_on_ensemble_predictions():
