@@ -158,11 +158,42 @@ class DYffusion(BaseModel):
         return self.sample_loop(initial_condition, **kwargs)[1]
 
     def p_losses(self, xt_last: Tensor, condition: Tensor, t: Tensor, static_condition: Tensor = None):
-        raise NotImplementedError("DYffusion training (p_losses) is the next tier (SURVEY.md 8f-1); this engine "
-                                  "builds the sampling path")
+        """The DYffusion objective (reference :496-567): forecaster loss on x_t (the initial condition for t = 0, an
+        interpolator sample for t > 0) plus, weighted `lambda_reconstruction2`, the loss of a second forecast from the
+        interpolation between the initial condition and the FIRST forecast at t + 1 (rows with t <= N - 2).
+
+        Forward only on the CUDA engine: this is the reference's validation loss (`val/loss`, `val/loss_forward[2]`, computed
+        under `torch.no_grad()` in eval mode).  The engine has no backward kernels yet, so calling it
+        with gradients enabled in train mode raises from the backbone's `forward`; around torch backbones (foreign
+        modules) it is differentiable as written."""
+        lam1, lam2 = self.hparams.lambda_reconstruction, self.hparams.lambda_reconstruction2
+        sub = lambda v, m: None if v is None else v[m]
+        x_t = condition.clone()
+        later = t > 0
+        if later.any():  # rows with t > 0 start from an interpolator sample at step t
+            x_ipol = self.q_sample(x_end=condition[later], x0=xt_last[later], t=t[later],
+                                   static_condition=sub(static_condition, later), num_predictions=1)
+            x_t[later] = x_ipol.to(x_t.dtype)
+        pred = self.predict_x_last(condition=condition, x_t=x_t, t=t, static_condition=static_condition)
+        loss_forward = self.criterion(pred, xt_last)
+        has_next = t <= self.num_timesteps - 2
+        loss_forward2 = 0.0
+        if lam2 > 0 and has_next.any():
+            t2 = t[has_next] + 1
+            cond2, static2 = condition[has_next], sub(static_condition, has_next)
+            x_ipol2 = self.q_sample(x_end=cond2, x0=pred[has_next], t=t2, static_condition=static2, num_predictions=1)
+            pred2 = self.predict_x_last(condition=cond2, x_t=x_ipol2, t=t2, static_condition=static2)
+            loss_forward2 = self.criterion(pred2, xt_last[has_next])
+        prefix = "train" if self.training else "val"
+        return {"loss": lam1 * loss_forward + lam2 * loss_forward2, f"{prefix}/loss_forward": loss_forward,
+                f"{prefix}/loss_forward2": loss_forward2}
 
     def forward(self, inputs, targets=None, condition=None, time=None):
-        return self.p_losses(targets, condition=inputs, t=time, static_condition=condition)
+        """reference _base_diffusion.py:81-106: a random diffusion step per row unless `time` is given."""
+        b = (targets if targets is not None else inputs).shape[0]
+        t = time if time is not None else torch.randint(0, self.num_timesteps, (b,), device=inputs.device,
+                                                         dtype=torch.long)
+        return self.p_losses(targets, condition=inputs, t=t, static_condition=condition)
 
     def get_loss(self, inputs, targets, metadata: Any = None, **kwargs):
         return self(inputs, targets, **kwargs)

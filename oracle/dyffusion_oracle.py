@@ -418,3 +418,53 @@ def count_calls(sched: Schedule, refine: bool, sampling_type: str = "cold",
     if refine:
         i += len([v for v in sched.dynamical_steps.values() if v < N])
     return f, i
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the training / validation objective -- src/diffusion/dyffusion.py:496-567 (p_losses); SURVEY.md 8f-1
+# ----------------------------------------------------------------------------------------------------------------
+def p_losses(forecaster: NetFn, interpolator: NetFn, sched: Schedule, xt_last: Tensor, condition: Tensor, t: Tensor,
+             static_condition: Optional[Tensor] = None, *, forward_conditioning: str = "data",
+             time_encoding: str = "dynamics", lambda_reconstruction: float = 0.5, lambda_reconstruction2: float = 0.5,
+             criterion: Callable[[Tensor, Tensor], Tensor] = torch.nn.functional.l1_loss,
+             noise_fn: Callable[[Tensor], Tensor] = torch.randn_like) -> Dict[str, Tensor]:
+    """`t` holds one integer diffusion step per row.  Returns {"loss", "loss_forward", "loss_forward2"}.
+    The interpolator / forecaster callables decide about dropout (the reference forces interpolator dropout on while
+    training or when `enable_interpolator_dropout`, :154-160)."""
+    N = sched.num_timesteps
+    tau = lambda steps: torch.tensor([float(sched.tau(int(s))) for s in steps], dtype=torch.float32)
+
+    def F_(x_t, cond_rows, static_rows, steps):  # predict_x_last (:205-239)
+        if forward_conditioning == "data":
+            c = cond_rows
+        elif forward_conditioning == "none":
+            c = None
+        else:
+            w = (steps / (N - 1)).view(-1, 1, 1, 1)
+            c = w * cond_rows + (1 - w) * noise_fn(cond_rows)
+        if static_rows is not None:
+            c = static_rows if c is None else torch.cat([c, static_rows], dim=1)
+        tt = {"discrete": steps.float(), "normalized": steps / N, "dynamics": tau(steps)}[time_encoding]
+        return forecaster(x_t, tt, c)
+
+    def I_(cond_rows, x_last_rows, static_rows, steps):  # q_sample (:140-163) -> _interpolate (:480-494)
+        times = tau(steps)
+        assert (0 < times).all() and (times < sched.tau(N - 1) + 1).all()
+        return interpolator(torch.cat([cond_rows, x_last_rows], dim=1), times, static_rows)
+
+    pick = lambda v, m: None if v is None else v[m]
+    x_t = condition.clone()                                                   # :512
+    nz = t > 0                                                                # :515-526
+    if nz.any():
+        x_t[nz] = I_(condition[nz], xt_last[nz], pick(static_condition, nz), t[nz])
+    pred = F_(x_t, condition, static_condition, t)                            # :530-532
+    loss1 = criterion(pred, xt_last)
+    nl = t <= N - 2                                                           # :535-557
+    loss2 = torch.zeros(())
+    if lambda_reconstruction2 > 0 and nl.any():
+        t2 = t[nl] + 1
+        x_i2 = I_(condition[nl], pred[nl], pick(static_condition, nl), t2)
+        pred2 = F_(x_i2, condition[nl], pick(static_condition, nl), t2)
+        loss2 = criterion(pred2, xt_last[nl])
+    return {"loss": lambda_reconstruction * loss1 + lambda_reconstruction2 * loss2, "loss_forward": loss1,
+            "loss_forward2": loss2}
