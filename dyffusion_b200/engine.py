@@ -79,6 +79,10 @@ def _load() -> C.CDLL:
         "dyf_boundary_conditions_navier_stokes": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dyf_boundary_conditions_spring_mesh": (C.c_int, [vp, vp, vp, C.c_int64, i32, i32, i32, vp]),
         "dyf_window_gather": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), i32, i32, vp, vp]),
+        "dyf_adamw_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(sz)]),
+        "dyf_grad_sq_norm": (C.c_int, [vp, C.c_int64, vp, vp, sz, vp]),
+        "dyf_adamw_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     C.c_int64, C.c_double, vp, sz, vp]),
         "dyf_profile_enable": (C.c_int, [i32]),
         "dyf_profile_filter": (C.c_int, [i32]),
         "dyf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -99,7 +103,8 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_cr
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
             "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read",
             "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics", "dyf_boundary_conditions_navier_stokes",
-            "dyf_boundary_conditions_spring_mesh", "dyf_window_gather"]
+            "dyf_boundary_conditions_spring_mesh", "dyf_window_gather", "dyf_adamw_workspace_bytes",
+            "dyf_grad_sq_norm", "dyf_adamw_step"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
                   "attention", "conv_up"]
 

@@ -211,6 +211,21 @@ int dyf_boundary_conditions_spring_mesh(float* preds, const uint8_t* fixed_mask,
 int dyf_window_gather(const float* frames, int64_t n_frames, int64_t frame_elems, const int64_t* first_frame_host, int32_t batch,
                       int32_t frames_per_example, float* out, void* stream);
 
+/* Widening row SURVEY.md 8f-1 (optimizer half) -- fused AdamW with global-norm gradient clipping over flat fp32 arrays.
+ * Replaces: `torch.optim.AdamW.step` of the optimizer `BaseExperiment._get_optim` builds
+ * (src/experiment_types/_base_experiment.py:711-725, src/configs/optimizer/adamw.yaml) preceded by Lightning's
+ * `gradient_clip_val` pass (src/configs/trainer/default.yaml:10; torch.nn.utils.clip_grad_norm_ semantics: every gradient
+ * scaled by min(1, max_norm / (||g||_2 + 1e-6)) over ALL parameters).  params / grads / exp_avg / exp_avg_sq: device arrays
+ * of n floats, 16-byte aligned (the host side keeps all tensors as views of four arenas); `step` counts from 1;
+ * `max_grad_norm` <= 0 disables clipping.  The squared norm is reduced on the device in a fixed order and consumed by
+ * the update kernel without a host round trip; `dyf_grad_sq_norm` exposes it ([1] double, device) for logging.
+ * Arithmetic: fp32, in the operation order of torch's single-tensor AdamW. */
+int dyf_adamw_workspace_bytes(int64_t n, size_t* bytes);
+int dyf_grad_sq_norm(const float* grads, int64_t n, double* out, void* workspace, size_t workspace_bytes, void* stream);
+int dyf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int64_t step, double max_grad_norm, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Test hook: writes the keep-mask (1/0 bytes) the engine's dropout draws for a tensor of `n_elems` elements
  * (NHWC element order, channel count `channels`) at (seed, stream, site, p).  Lets tests replay engine masks in
  * the oracle. */
