@@ -65,3 +65,19 @@ def sample_sharded(diffusion, initial_condition: torch.Tensor, static_condition:
         local = initial_condition.new_zeros((len(keys), 0, c, *initial_condition.shape[2:]))
     full = gather_rows(local, rows, group=group)
     return {k: full[i] for i, k in enumerate(keys)}
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data-parallel gradient synchronisation for the training tier: Lightning's DDP averages the
+    gradients in ~25 MB buckets while the backward runs (`trainer=ddp`); with `dyffusion_b200.optim.AdamW` every gradient is a
+    view of ONE flat arena, so the whole exchange is a single in-place all-reduce of that arena (NCCL picks NVLS / ring over
+    NVSwitch; one launch, no bucketing logic) followed by the 1/world scale.  No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return flat
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat

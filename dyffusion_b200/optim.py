@@ -129,6 +129,14 @@ class AdamW(torch.optim.Optimizer):
             o.mark_dirty()
         return loss
 
+    def sync_gradients(self, process_group=None) -> None:
+        """DDP's gradient averaging as one all-reduce per arena (`dyffusion_b200.distributed.allreduce_mean_`); call it
+        between `backward()` and `step()` -- the clip then sees the averaged gradients, as under Lightning's DDP."""
+        from .distributed import allreduce_mean_
+        for group, arena in zip(self.param_groups, self._arenas):
+            self._collect_grads(group, arena)
+            allreduce_mean_(arena.grads, process_group)
+
     def grad_norm(self, group: int = 0) -> torch.Tensor:
         """Global L2 norm of the gradients seen by the last clipped `step` (device scalar; Lightning logs `grad_norm`)."""
         return self._arenas[group].workspace[-1].sqrt()

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dyffusion_b200.distributed import gather_rows, sample_sharded, shard_bounds
+from dyffusion_b200.distributed import allreduce_mean_, gather_rows, sample_sharded, shard_bounds
 
 
 class _FakeDiffusion:
@@ -16,6 +16,32 @@ class _FakeDiffusion:
     def sample(self, ic, static_condition=None, **kw):
         s = 0 if static_condition is None else static_condition.sum(dim=1, keepdim=True)
         return {f"t{i}_preds": ic[:, -3:] * i + s for i in (1, 2, 3)}
+
+
+def _rollout_is_rank_invariant(rows):
+    """The autoregressive rollout with its sampler calls sharded over the ranks returns, on every rank, what one process
+    returns: member-major row order survives shard -> all-gather -> (N, B) un-stacking -> hand-off."""
+    from dyffusion_b200.rollout import MultiHorizonRollout
+
+    class Diff(_FakeDiffusion):
+        num_timesteps = 3
+        hparams = {"timesteps": 3}
+
+        def sample_loop(self, initial_condition, static_condition=None, log_every_t=None, num_predictions=None):
+            raise NotImplementedError
+
+        def predict_forward(self, inputs, condition=None, metadata=None, **kw):
+            return self.sample(inputs, static_condition=condition)
+
+    members = 2
+    g = torch.Generator().manual_seed(1)
+    batch = {"dynamics": torch.randn(rows, 7, 3, 5, 4, generator=g), "condition": torch.randn(rows, 2, 5, 4, generator=g)}
+    bc = lambda preds, targets, metadata, time: preds.mul_(0.5).add_(time)
+    kw = dict(horizon=3, num_predictions=members, autoregressive_steps=1)
+    want = MultiHorizonRollout(Diff(), **kw).evaluation_step(batch, "test", boundary_conditions=bc)
+    got = MultiHorizonRollout(Diff(), group=dist.group.WORLD, **kw).evaluation_step(batch, "test", boundary_conditions=bc)
+    return list(got) == list(want) and all(torch.equal(got[k], want[k]) for k in want) and \
+        tuple(got["t6_preds"].shape) == (members, rows, 3, 5, 4)
 
 
 def _worker(rank, world, port, rows, q):
@@ -33,6 +59,11 @@ def _worker(rank, world, port, rows, q):
         local = torch.arange(b, e, dtype=torch.float32).view(1, -1, 1).repeat(2, 1, 3)
         full = gather_rows(local, rows)
         ok = ok and torch.equal(full[0, :, 0], torch.arange(rows, dtype=torch.float32)) and full.shape == (2, rows, 3)
+        # gradient arena: one in-place all-reduce = the mean over ranks (DDP semantics)
+        arena = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        allreduce_mean_(arena)
+        ok = ok and torch.equal(arena, torch.arange(10, dtype=torch.float32) * 1.5)
+        ok = ok and _rollout_is_rank_invariant(rows)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
