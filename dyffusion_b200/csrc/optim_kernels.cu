@@ -37,12 +37,14 @@ __global__ void __launch_bounds__(OT) grad_sq_partial_kernel(const float* __rest
   }
 }
 
-__global__ void grad_sq_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int b = 0; b < blocks; ++b) t += partial[b];  // fixed order: bit-reproducible
-    out[0] = t;
-  }
+// One warp; lane l adds partial[l], partial[l + 32], ... in that order, then a fixed butterfly: bit-reproducible, and the loads
+// of a lane are independent (a single thread walking the 1 184 partials took 48 us, a quarter of the whole step).
+__global__ void __launch_bounds__(32) grad_sq_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
+  double t = 0.0;
+  for (int b = threadIdx.x; b < blocks; b += 32) t += partial[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[0] = t;
 }
 
 struct AdamArgs {
@@ -121,11 +123,9 @@ int dyf_grad_sq_norm(const float* grads, int64_t n, double* out, void* workspace
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: dyffusion_b200 has no CPU fallback"); return DYF_ERR_CUDA; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   double* partial = reinterpret_cast<double*>(workspace);
-  {
-    ProfScope prof(s, KC_ELEMENTWISE, 0.0, 4.0 * (double)n);
-    grad_sq_partial_kernel<<<blocks, OT, 0, s>>>(grads, n, partial);
-    DYF_LAUNCH_OK("grad_sq_partial_kernel");
-  }
+  ProfScope prof(s, KC_ELEMENTWISE, 0.0, 4.0 * (double)n);
+  grad_sq_partial_kernel<<<blocks, OT, 0, s>>>(grads, n, partial);
+  DYF_LAUNCH_OK("grad_sq_partial_kernel");
   grad_sq_final_kernel<<<1, 32, 0, s>>>(partial, blocks, out);
   DYF_LAUNCH_OK("grad_sq_final_kernel");
   return 0;
