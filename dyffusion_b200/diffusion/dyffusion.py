@@ -303,15 +303,14 @@ class DYffusion(BaseModel):
         x_s = initial_condition[:, -self.num_input_channels:]
         out, x0_hat, key = {}, None, 0
         after_last = sched[-1] + 1
-        x_next = None
-        for s, s_next in zip(sched, sched[1:] + [after_last]):
+        x_next = x_cur = None  # x_cur deliberately survives the iteration: on a last step without cold sampling the
+        for s, s_next in zip(sched, sched[1:] + [after_last]):  # reference logs the PREVIOUS step's D(x_s, s) (:401-406)
             last = s == N - 1
             x0_hat = self.predict_x_last(condition=initial_condition, x_t=x_s, t=full(s), is_sampling=True, **sc)
             t_next = self.diffusion_step_to_interpolation_step(s_next) if not last else np.inf
             dyn = float(t_next).is_integer() or last
             qkw = dict(x0=x0_hat, x_end=initial_condition, is_artificial_step=not dyn)
             x_next = self.q_sample(**qkw, t=full(s_next), **sc) if s_next <= N - 1 else x0_hat
-            x_cur = None
             if self.hparams.sampling_type == "cold":
                 if last and not self.hparams.use_cold_sampling_for_last_step:
                     x_s = x0_hat
