@@ -11,8 +11,6 @@
 // is one example; threads stream its run with the widest access both the run start and the output allow
 // (16 B when frame_elems % 4 == 0; 16-byte stores with 16- or 2 x 8-byte loads when it is even -- Navier-Stokes frames hold
 // 3*221*42 = 27 846 floats; else 4 B), 64 bytes of independent loads in flight per thread before the stores.
-#include <cstdlib>
-
 #include "engine.hpp"
 
 namespace dyf {
@@ -150,7 +148,7 @@ int dyf_window_gather(const float* frames, int64_t n_frames, int64_t frame_elems
   const uintptr_t a = reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(out);
   // every run start is a multiple of frame_elems floats from an aligned base, every output start a multiple of run
   if (frame_elems % 4 == 0 && a % 16 == 0) return launch_gather<float4>(frames, out, run, frame_elems, first_frame_host, batch, s);
-  if (frame_elems % 2 == 0 && a % 16 == 0 && !getenv("DYF_GATHER_8B"))
+  if (frame_elems % 2 == 0 && a % 16 == 0)
     return launch_gather<float4, true>(frames, out, run, frame_elems, first_frame_host, batch, s);
   if (frame_elems % 2 == 0 && a % 8 == 0) return launch_gather<float2>(frames, out, run, frame_elems, first_frame_host, batch, s);
   return launch_gather<float>(frames, out, run, frame_elems, first_frame_host, batch, s);

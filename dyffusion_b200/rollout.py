@@ -28,11 +28,6 @@ import torch
 from torch import Tensor
 
 
-def _key(v) -> str:
-    """f-string formatting of a horizon exactly as the reference's keys (`f"t{t_step}_preds"` with numpy/py numbers)."""
-    return f"{v}"
-
-
 class MultiHorizonRollout:
     """Evaluation-time mirror of `MultiHorizonForecastingDYffusion` (forecasting_multi_horizon.py:391-424) around a
     DYffusion sampler.  Constructor arguments carry the reference's names: `horizon`/`window` are the datamodule's,
@@ -219,7 +214,7 @@ class MultiHorizonRollout:
                                                             autoregressive_inputs=autoregressive_inputs)
             with torch.no_grad():
                 self._current_preds = self.predict(inputs, **extra, **kwargs)
-        preds_key = f"t{_key(horizon)}_preds"
+        preds_key = f"t{horizon}_preds"
         results = {k: self._current_preds.pop(k) for k in list(self._current_preds.keys()) if preds_key in k}
         if horizon == self.horizon_range[-1]:
             assert all(["preds" not in k for k in self._current_preds.keys()]), (
@@ -265,16 +260,16 @@ class MultiHorizonRollout:
                     targets = dynamics[:, self.window + int(total_horizon) - 1, ...]
                 else:
                     targets = None
-                pk = f"t{_key(t_step)}_preds"
+                pk = f"t{t_step}_preds"
                 if boundary_conditions is not None:
                     results[pk] = boundary_conditions(preds=results[pk], targets=targets,
                                                       metadata=batch.get("metadata", None), time=total_t)
                 preds = results.pop(pk)
                 if return_outputs in [True, "all"]:
-                    return_dict[f"t{_key(total_horizon)}_targets"] = conv(targets)
-                    return_dict[f"t{_key(total_horizon)}_preds"] = conv(preds)
+                    return_dict[f"t{total_horizon}_targets"] = conv(targets)
+                    return_dict[f"t{total_horizon}_preds"] = conv(preds)
                 if return_outputs == "all":
-                    return_dict.update({k.replace(f"t{_key(t_step)}", f"t{_key(total_horizon)}"): conv(v)
+                    return_dict.update({k.replace(f"t{t_step}", f"t{total_horizon}"): conv(v)
                                         for k, v in results.items()})
                 if t_step in ar_window_steps_t:
                     ar_window_steps += [preds.reshape(-1, *preds.shape[-3:]).unsqueeze(1)]
