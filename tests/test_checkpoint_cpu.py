@@ -64,3 +64,38 @@ def test_against_the_real_reference_modules(dataset):
         assert torch.equal(parts["model"][k], v)
     plain = split_state_dict(interp.state_dict())
     assert sorted(plain["model"]) == sorted(interp.model.state_dict())
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("kind", ["dyffusion", "plain"])
+def test_ema_weights_against_the_real_litema(kind):
+    """`use_ema=True`: the shadow names are not guessed either -- the reference's own `LitEma` (src/models/modules/ema.py) is
+    built over the reference module, stepped, and its buffers are what a `use_ema` run stores under `model_ema.`; the weights
+    the reference would evaluate with (`LitEma.copy_to`, via `ema_scope`) must be what the ingest returns."""
+    from oracle import ref_build
+    ref_shims.install()
+    from src.models.modules.ema import LitEma
+    interp = ref_build.build_interpolator("spring", horizon=3)
+    exp = ref_build.build_dyffusion("spring", interp, horizon=3) if kind == "dyffusion" else interp
+    ema = LitEma(exp.model, decay=0.9)
+    with torch.no_grad():
+        for p in exp.model.parameters():
+            if p.requires_grad:
+                p.add_(0.5 * torch.randn_like(p))
+    ema(exp.model)  # one EMA update: the shadows now differ from both the initial and the current weights
+    sd = {k: v.clone() for k, v in {**exp.state_dict(), **{"model_ema." + k: v for k, v in ema.state_dict().items()}}.items()}
+    plain_parts = split_state_dict(sd)
+    ema_parts = split_state_dict(sd, use_ema=True)
+    backbone = exp.model.model if kind == "dyffusion" else exp.model
+    want = {k: v.clone() for k, v in backbone.state_dict().items()}
+    ema.copy_to(exp.model)  # what ema_scope does before evaluating
+    swapped = 0
+    for k, v in backbone.state_dict().items():
+        assert torch.equal(ema_parts["model"][k], v), k
+        assert torch.equal(plain_parts["model"][k], want[k]), k
+        swapped += int(not torch.equal(v, want[k]))
+    assert swapped == sum(1 for p in backbone.parameters() if p.requires_grad)  # every trainable tensor, no buffer
+    if kind == "dyffusion":  # the frozen interpolator has no shadows and is returned as stored
+        assert all(torch.equal(ema_parts["interpolator"][k], v) for k, v in interp.model.state_dict().items())
+    with pytest.raises(ValueError):
+        split_state_dict(exp.state_dict(), use_ema=True)  # a run without use_ema
