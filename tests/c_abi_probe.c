@@ -35,7 +35,7 @@ int main(void) {
     if (strcmp(dyf_net_param_key(net, i), "time_emb_mlp.1.weight") == 0) found = 1;  /* reference state-dict key */
   EXPECT(found);
   EXPECT(dyf_net_set_param(net, "no.such.key", dummy, &first, 1) < 0 && strlen(dyf_last_error()) > 0);
-  EXPECT(dyf_net_finalize(net, NULL) < 0);  /* parameters were never set: strict, names the missing key */
+  EXPECT(dyf_net_finalize(net, NULL) < 0);  /* no device here; on a GPU box: parameters never set, names the first missing key */
   printf("finalize: %s\n", dyf_last_error());
   dyf_net_destroy(net);
 
