@@ -64,13 +64,27 @@ def _bn_eval(sd: SD, key: str, x: Tensor) -> Tensor:
                         sd[f"{key}.bias"], training=False, eps=1e-5)
 
 
+def _bn(sd: SD, key: str, x: Tensor, train_stats: Optional[Dict[str, Tensor]]) -> Tensor:
+    """nn.BatchNorm2d.  `train_stats is None`: eval mode (running statistics; what sampling uses).  Otherwise train mode
+    (SURVEY.md 8f-1): normalise with the batch mean / biased batch variance and write the running statistics after the
+    momentum-0.1 update (unbiased variance) into `train_stats` -- chained through it when a net is called more than once, as
+    in `p_losses`."""
+    if train_stats is None:
+        return _bn_eval(sd, key, x)
+    rm = train_stats.get(f"{key}.running_mean", sd[f"{key}.running_mean"]).clone()
+    rv = train_stats.get(f"{key}.running_var", sd[f"{key}.running_var"]).clone()
+    y = F.batch_norm(x, rm, rv, sd[f"{key}.weight"], sd[f"{key}.bias"], training=True, momentum=0.1, eps=1e-5)
+    train_stats[f"{key}.running_mean"], train_stats[f"{key}.running_var"] = rm, rv
+    return y
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Navier-Stokes backbone -- src/models/unet_simple.py:13-197
 # ----------------------------------------------------------------------------------------------------------------
 def unet_simple_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], condition: Optional[Tensor], *,
                         dim: int = 64, upsample_dims: Optional[Sequence[int]] = (256, 256),
                         outer_sample_mode: str = "bilinear", dropout: float = 0.0, input_dropout: float = 0.0,
-                        drop: DropFn = None) -> Tensor:
+                        drop: DropFn = None, train_stats: Optional[Dict[str, Tensor]] = None) -> Tensor:
     x = inputs if condition is None else torch.cat([inputs, condition], dim=1)  # inputs first (:184)
     temb = time_embedding(sd, time, dim) if "time_emb_mlp.1.weight" in sd else None
     hw = x.shape[-2:]
@@ -84,7 +98,7 @@ def unet_simple_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], conditio
         p = f"input_ops.{i}"
         x = F.conv2d(x, sd[f"{p}.ops.0.weight"], sd[f"{p}.ops.0.bias"], stride=2, padding=pad)
         if f"{p}.ops.1.running_mean" in sd:
-            x = _bn_eval(sd, f"{p}.ops.1", x)
+            x = _bn(sd, f"{p}.ops.1", x, train_stats)
         else:  # last encoder block uses GroupNorm(8) (:56, :128)
             x = F.group_norm(x, 8, sd[f"{p}.ops.1.weight"], sd[f"{p}.ops.1.bias"], eps=1e-5)
         if temb is not None:
@@ -99,7 +113,7 @@ def unet_simple_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], conditio
         p = f"output_ops.{i}"
         x = F.interpolate(x, scale_factor=2, mode="bilinear")
         x = F.conv2d(x, sd[f"{p}.ops.1.weight"], sd[f"{p}.ops.1.bias"], stride=1, padding=pad)
-        x = _bn_eval(sd, f"{p}.ops.2", x)
+        x = _bn(sd, f"{p}.ops.2", x, train_stats)
         if temb is not None:
             sc, sh = _scale_shift(sd, f"{p}.time_mlp.1", temb)
             x = x * (sc + 1) + sh
@@ -118,7 +132,8 @@ def unet_simple_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], conditio
 # ----------------------------------------------------------------------------------------------------------------
 def simple_conv_net_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], condition: Optional[Tensor], *,
                             dim: int = 64, kernel_sizes: Sequence[int] = (9, 7, 5, 3), residual: bool = True,
-                            dropout: float = 0.0, drop: DropFn = None) -> Tensor:
+                            dropout: float = 0.0, drop: DropFn = None,
+                            train_stats: Optional[Dict[str, Tensor]] = None) -> Tensor:
     x = inputs if condition is None else torch.cat([inputs, condition], dim=1)  # (:121)
     temb = time_embedding(sd, time, dim) if "time_emb_mlp.1.weight" in sd else None
     for i, k in enumerate(kernel_sizes):
@@ -126,7 +141,7 @@ def simple_conv_net_forward(sd: SD, inputs: Tensor, time: Optional[Tensor], cond
         res = x
         w = sd[f"{p}.conv.weight"]
         x = F.conv2d(x, w, sd[f"{p}.conv.bias"], padding=(k - 1) // 2)
-        x = _bn_eval(sd, f"{p}.norm", x)
+        x = _bn(sd, f"{p}.norm", x, train_stats)
         if temb is not None:
             sc, sh = _scale_shift(sd, f"{p}.time_mlp.1", temb)
             x = x * (sc + 1) + sh
