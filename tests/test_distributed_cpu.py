@@ -62,26 +62,37 @@ def _worker(rank, world, port, rows, q):
         # gradient arena: one in-place all-reduce = the mean over ranks (DDP semantics)
         arena = torch.arange(10, dtype=torch.float32) * (rank + 1)
         allreduce_mean_(arena)
-        ok = ok and torch.equal(arena, torch.arange(10, dtype=torch.float32) * 1.5)
+        ok = ok and torch.allclose(arena, torch.arange(10, dtype=torch.float32) * ((world + 1) / 2))
         ok = ok and _rollout_is_rank_invariant(rows)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("rows", [8, 5, 1])
-def test_sharded_sampling_world2(rows):
+def _run_world(world, rows):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + rows) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * rows + 131 * world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
+        p.join(180)
         assert p.exitcode == 0
-    res = dict(q.get(timeout=10) for _ in range(2))
-    assert res == {0: True, 1: True}
+    res = dict(q.get(timeout=10) for _ in range(world))
+    assert res == {r: True for r in range(world)}
+
+
+@pytest.mark.parametrize("rows", [8, 5, 1])
+def test_sharded_sampling_world2(rows):
+    _run_world(2, rows)
+
+
+@pytest.mark.parametrize("rows", [6, 3])
+def test_sharded_sampling_world4_with_short_and_empty_shards(rows):
+    """6 rows over 4 ranks -> shards of 2, 2, 2, 0; 3 rows -> 1, 1, 1, 0: the last rank owns no rows and still takes part in
+    the all-gather (keys come from rank 0), every rank ends with all rows in the global order."""
+    _run_world(4, rows)
 
 
 def test_shard_bounds():
