@@ -225,7 +225,10 @@ def unet_resnet_forward(sd: SD, x: Tensor, time: Optional[Tensor], condition: Op
                         dim: int = 64, dim_mults: Sequence[int] = (1, 2, 4), groups: int = 8,
                         block_dropout: float = 0.0, block_dropout1: float = 0.0, attn_dropout: float = 0.0,
                         input_dropout: float = 0.0, keep_spatial_dims: bool = False, init_padding: int = 3,
-                        init_stride: int = 1, drop: DropFn = None) -> Tensor:
+                        init_stride: int = 1, drop: DropFn = None,
+                        train_stats: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    # `train_stats` is accepted for a uniform signature and unused: GroupNorm / weight standardisation / channel LayerNorm
+    # carry no batch statistics, so train mode differs from eval mode only through dropout
     if condition is not None:
         x = torch.cat([condition, x], dim=1)  # condition FIRST (unet.py:269)
     x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], stride=init_stride, padding=init_padding)
