@@ -88,6 +88,11 @@ class AdamW(torch.optim.Optimizer):
             self._arenas.append(arena)
 
     # ------------------------------------------------------------------ torch.optim.Optimizer surface
+    def add_param_group(self, param_group) -> None:
+        if getattr(self, "_arenas", None):  # torch calls this during construction; later additions cannot join an arena
+            raise NotImplementedError("parameter groups are laid out in flat arenas at construction: build a new optimizer")
+        super().add_param_group(param_group)
+
     def zero_grad(self, set_to_none: bool = False) -> None:
         """One memset per group; the gradient views stay attached (`set_to_none` would detach them and is ignored)."""
         for group, arena in zip(self.param_groups, self._arenas):
