@@ -90,6 +90,12 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
+def workload(rows):
+    """`config.workload` of both arms (the reference arm times a bounded sample of it, named in its `cpu_baseline.sample`)."""
+    return (f"NS 221x42 DYffusion sampling h=16, {rows} rows/GPU (BASELINE configs[1]): 16 forecaster + 44 interpolator "
+            "unet_simple forwards, cold sampling + refinement, interpolator dropout 0.15")
+
+
 def synth_inputs(rows, seed):
     from oracle.synth import synth_tensor
     ic = synth_tensor(f"bench.ic{seed}", (rows, 3, H, W))
@@ -142,7 +148,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "NS 221x42 DYffusion sampling h=16 (unet_simple x2, cold+refine), CPU rows=1/step"},
+        "config": {"workload": workload(args.rows), "rows_per_gpu": args.rows,
+                   "sample": "the reference's CPU path is timed on rows=1 per step of this workload (same networks, schedule, "
+                             "refinement, dropout); throughput is per row, so the bounded sample does not bias it"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -258,10 +266,7 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"NS 221x42 DYffusion sampling h=16, {rows} rows/GPU (BASELINE configs[1]): "
-                                   "16 forecaster + 44 interpolator unet_simple forwards, cold sampling + refinement, "
-                                   "interpolator dropout 0.15",
-                       "rows_per_gpu": rows, "l2": "working set >> L2 (>= 5 GB of activations per network forward)",
+            "config": {"workload": workload(rows), "rows_per_gpu": rows, "l2": "working set >> L2 (>= 5 GB of activations per network forward)",
                        "operands": "bf16 operands, fp32 accumulate/epilogue, fp32 sampler state"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(ic_pin.numel() * 4 + st_pin.numel() * 4),
                     "d2h_bytes_per_step": int(host_out.numel() * 4)},

@@ -1,0 +1,34 @@
+"""The reference arm of bench.py (`--impl reference`: the reference's CPU implementation of the path, oracle port, all host
+threads) runs without a GPU: check its ONE JSON line against the driver's contract, and that both arms name the same workload."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["unit"] == "cell-steps/s" and "Navier-Stokes 221x42 h=16" in d["metric"]
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert abs(d["value"] - 221 * 42 * 16 / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]  # rows=1 per step
+    cb, e2e = d["cpu_baseline"], d["e2e"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rows=1" in cb["sample"]
+    assert e2e == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.workload(bench.ROWS) and "BASELINE configs[1]" in d["config"]["workload"]
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
