@@ -12,7 +12,8 @@ What changes against the reference is WHERE things happen, not what is computed:
   converts every horizon with `torch_to_numpy`, :185-187) and nothing synchronises the stream;
 * results are device tensors (`to_numpy=True` restores the reference's numpy dict);
 * the caller's `batch["dynamics"]` is NOT multiplied by 1e6 after the first pass (:221 is a debugging guard; the targets
-  come from a clone taken before the loop in the reference, so no result depends on it).
+  come from a clone taken before the loop in the reference, so no result depends on it), and a tensor `t0` is not advanced in
+  place (the reference's `total_t += ...` (:164) writes into the caller's `metadata["t"][:, 0]`).
 
 The host logic is written against the `diffusion` object's `predict_forward` / `sample_loop` surface only, so the tests
 drive it on CPU around the reference's own DYffusion module and compare with the reference loop bit for bit
