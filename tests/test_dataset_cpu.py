@@ -69,3 +69,32 @@ def test_errors_and_no_cpu_fallback():
     ds = TrajectoryWindows(trajs, 1, 3, "spring-mesh", device="cpu")
     with pytest.raises(E.EngineError):  # the gather has no CPU path
         ds.get_batch([0, 1])
+
+
+@pytest.mark.needs_reference
+def test_random_stores_against_the_reference_method():
+    """Random trajectory counts / lengths / windows / horizons (spring-mesh sized frames): oracle == reference method, and the
+    product's index arithmetic addresses exactly the reference's examples."""
+    import random
+    ref_shims.install()
+    from src.datamodules.physical_systems_benchmark import PhysicalSystemsBenchmarkDataModule as DM
+    rng = random.Random(3)
+    for trial in range(12):
+        window, horizon = rng.randint(1, 3), rng.randint(1, 6)
+        lengths = [window + horizon + rng.randint(0, 7) for _ in range(rng.randint(1, 4))]
+        cap = rng.choice([None, None, 1, 2])
+        trajs = H.synth_trajectories("spring-mesh", lengths, seed=trial)
+        fake = types.SimpleNamespace(hparams=types.SimpleNamespace(window=window, horizon=horizon, num_trajectories=cap,
+                                                                   physical_system="spring-mesh"),
+                                     get_horizon=lambda split, h=horizon: h)
+        want = DM.create_dataset_multi_horizon(fake, "train", trajs, keep_trajectory_dim=False)
+        got = dataset_oracle.create_dataset_multi_horizon(trajs, window, horizon, num_trajectories=cap)
+        assert np.array_equal(got["dynamics"], want["dynamics"]) and np.array_equal(got["condition"], want["condition"])
+        ds = TrajectoryWindows(trajs, window, horizon, "spring-mesh", num_trajectories=cap, device="cpu")
+        assert len(ds) == want["dynamics"].shape[0]
+        first, tr = ds.first_frames(range(len(ds)))
+        store = ds.frames.numpy()
+        for g in rng.sample(range(len(ds)), min(len(ds), 6)):
+            assert np.array_equal(store[first[g]:first[g] + window + horizon], want["dynamics"][g])
+            assert np.array_equal(ds.conditions[tr[g]].numpy(), want["condition"][g])
+            assert want["metadata"][g]["name"] == trajs[tr[g]].trajectory_meta["name"]
