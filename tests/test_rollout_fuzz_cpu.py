@@ -36,7 +36,7 @@ class FakeDiffusion(torch.nn.Module):
         return {f"t{i}_preds": torch.tanh(last * (0.5 + 0.1 * i) + 0.3 * whole + 0.01 * s) for i in range(1, self.horizon + 1)}
 
 
-def _reference_experiment(horizon, window, members, ar_steps, prediction_horizon):
+def _reference_experiment(horizon, window, members, ar_steps, prediction_horizon, noise=0.0):
     from oracle import ref_build
     saved = C.DATASETS["spring"]["datamodule"]["window"]
     C.DATASETS["spring"]["datamodule"]["window"] = window
@@ -47,6 +47,7 @@ def _reference_experiment(horizon, window, members, ar_steps, prediction_horizon
         C.DATASETS["spring"]["datamodule"]["window"] = saved
     exp.hparams.num_predictions = members
     exp.hparams.autoregressive_steps = ar_steps
+    exp.hparams.prediction_inputs_noise = noise
     if prediction_horizon is not None:
         exp.datamodule_config["prediction_horizon"] = prediction_horizon
     exp.model = FakeDiffusion(horizon)
@@ -83,15 +84,18 @@ def test_rollout_agrees_with_the_reference_on_random_configurations():
                 return preds
             return bc
 
-        exp = _reference_experiment(horizon, window, members, ar_steps, pred_h)
+        noise = rng.choice([0.0, 0.0, 0.1])  # `prediction_inputs_noise`: per-member input noise from the torch RNG (:523-528)
+        exp = _reference_experiment(horizon, window, members, ar_steps, pred_h, noise)
+        torch.manual_seed(100 + trial)
         want = exp._evaluation_step({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch_d.items()}, 0, "test",
                                     boundary_conditions=make_bc(times["ref"]),
                                     t0=t0.clone() if torch.is_tensor(t0) else t0, dt=dt)  # the reference's `total_t +=` writes into t0
         fake = FakeDiffusion(horizon)
         ro = MultiHorizonRollout(fake, horizon=horizon, window=window, num_predictions=members, autoregressive_steps=ar_steps,
-                                 prediction_horizon=pred_h)
+                                 prediction_horizon=pred_h, prediction_inputs_noise=noise)
+        torch.manual_seed(100 + trial)
         got = ro.evaluation_step(batch_d, "test", boundary_conditions=make_bc(times["mine"]), t0=t0, dt=dt, to_numpy=True)
-        cfg = dict(horizon=horizon, window=window, members=members, batch=batch, ar_steps=ar_steps, pred_h=pred_h)
+        cfg = dict(horizon=horizon, window=window, members=members, batch=batch, ar_steps=ar_steps, pred_h=pred_h, noise=noise)
         assert list(got) == list(want), cfg
         for k in want:
             assert np.array_equal(got[k], want[k]), (cfg, k)
