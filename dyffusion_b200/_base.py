@@ -106,6 +106,40 @@ class BaseModel(EngineModule):
         self.ema_scope = None
         self._inference_dropout = False
 
+    # ---- `ema_scope` is assigned by the reference's BaseExperiment (src/experiment_types/_base_experiment.py:107).  Its
+    # LitEma swaps weights with `param.data.copy_()` (src/models/modules/ema.py:48-78), which no version counter sees, so the
+    # EMA object's copy_to / restore are wrapped to flag the engine's packed weights as stale.
+    @property
+    def ema_scope(self):
+        return self.__dict__.get("_ema_scope")
+
+    @ema_scope.setter
+    def ema_scope(self, fn):
+        self.__dict__["_ema_scope"] = fn
+        ema = getattr(getattr(fn, "__self__", None), "model_ema", None)
+        if ema is None or getattr(ema, "_dyf_hooked", False):
+            return
+        for name in ("copy_to", "restore"):
+            orig = getattr(ema, name, None)
+            if orig is None:
+                continue
+
+            def hooked(*a, _orig=orig, **k):
+                out = _orig(*a, **k)
+                self.mark_engine_dirty()
+                return out
+
+            object.__setattr__(ema, name, hooked)
+        object.__setattr__(ema, "_dyf_hooked", True)
+
+    def mark_engine_dirty(self) -> None:
+        """Force a re-pack of every engine backbone under this module before its next call.  Needed only after writes that
+        bypass autograd's version counters (`param.data.copy_()`, `param.data = ...` keeping the storage); optimizer steps,
+        nn.init, load_state_dict, .to()/.half() and the reference's EMA scope are detected automatically."""
+        for m in self.modules():
+            if hasattr(m, "_dirty"):
+                m._dirty = True
+
     # ---- reference surface (:77-175)
     @property
     def short_description(self) -> str:
@@ -160,6 +194,8 @@ class EngineBackbone(BaseModel):
         self._dirty = True
         self._drop_stream = 0
         self._specs = self._net.param_specs()
+        self._spec_keys = {s[0] for s in self._specs}
+        self._packed_fp = None
         for key, shape, is_buffer in self._specs:
             self._register(key, shape, is_buffer)
         self.reset_parameters()
@@ -215,20 +251,35 @@ class EngineBackbone(BaseModel):
     def mark_dirty(self) -> None:
         self._dirty = True
 
+    def _fingerprint(self, own) -> tuple:
+        """(storage pointer, in-place version counter) of every tensor the engine packed: any in-place write -- an optimizer
+        step, `p.data.copy_()`, nn.init, the reference's `ema_scope` (LitEma.copy_to / restore, src/models/modules/ema.py) --
+        bumps `_version`; a re-assigned `.data` changes the pointer."""
+        return tuple((v.data_ptr(), v._version) for v in own.values())
+
     def sync_engine(self) -> E.NetHandle:
-        if self._dirty or not self._net.finalized:
-            own = {k: v for k, v in self.state_dict().items() if k in {s[0] for s in self._specs}}
-            self._net.load(own)
+        """Re-pack the engine's weights whenever the nn.Parameters / buffers changed since the last pack."""
+        keys = self._spec_keys
+        own = {k: v for k, v in self.state_dict(keep_vars=True).items() if k in keys}
+        fp = self._fingerprint(own)
+        if self._dirty or not self._net.finalized or fp != self._packed_fp:
+            dev = next(iter(own.values())).device
+            if dev.type != "cuda":
+                raise E.EngineError(f"dyffusion_b200 has no CPU path: move the module to a CUDA device first (parameters on {dev})")
+            with torch.cuda.device(dev):  # pack on the GPU that owns the parameters, whatever the current device is
+                self._net.load({k: v.detach() for k, v in own.items()})
             self._dirty = False
+            self._packed_fp = fp
         return self._net
 
-    def _dropout_arg(self):
+    def _dropout_arg(self, row_offset: int = 0):
         if not (self._inference_dropout or self.training):
             return None
         self._drop_stream += 1
-        return (int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, self._drop_stream)
+        return (int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF, self._drop_stream, int(row_offset))
 
-    def forward(self, inputs, time=None, condition=None, return_time_emb: bool = False, **kwargs):
+    def forward(self, inputs, time=None, condition=None, return_time_emb: bool = False, row_offset: int = 0, **kwargs):
+        """`row_offset`: index of row 0 in the un-sharded job (dropout masks are functions of the global row)."""
         if return_time_emb:
             raise NotImplementedError("return_time_emb=True is not exposed by the engine")
         if self.num_conditional_channels == 0 and condition is not None:
@@ -237,4 +288,4 @@ class EngineBackbone(BaseModel):
             raise NotImplementedError("training through the CUDA engine is not built yet (SURVEY.md 8f-1); "
                                       "use torch.no_grad()/eval() for sampling")
         net = self.sync_engine()
-        return net.forward(inputs, time, condition, dropout=self._dropout_arg())
+        return net.forward(inputs, time, condition, dropout=self._dropout_arg(row_offset))

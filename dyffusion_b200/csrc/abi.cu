@@ -1,5 +1,9 @@
 // extern "C" surface of the engine (include/dyffusion_b200.h).
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -11,6 +15,18 @@ static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_counter() { return g_launches.load(); }
+
+// ---- NVTX ranges around network calls / sampler runs (nvtx3 is header-only and resolves the tool at run time)
+static bool g_nvtx = getenv("DYF_NVTX") != nullptr && getenv("DYF_NVTX")[0] == '1';
+NvtxRange::NvtxRange(const char* what, int arch, int rows) : on(g_nvtx) {
+  if (!on) return;
+  static const char* names[] = {"unet_simple", "unet_resnet", "convnet"};
+  char buf[96];
+  snprintf(buf, sizeof buf, "%s %s rows=%d", what, arch >= 0 && arch < 3 ? names[arch] : "?", rows);
+  nvtxRangePushA(buf);
+}
+NvtxRange::~NvtxRange() { if (on) nvtxRangePop(); }
 
 // ---- launch profiler
 struct ProfRec { cudaEvent_t a, b; int klass; double flops, bytes; };
@@ -18,6 +34,7 @@ static bool g_prof_on = false;
 static int g_prof_only = -1;  // -1 = every kernel class, else only launches of this class are bracketed by events
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
+bool profiling_enabled() { return g_prof_on; }
 static cudaEvent_t take_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;
@@ -51,6 +68,8 @@ static int require_device() {
 extern "C" {
 
 int dyf_abi_version(void) { return DYF_ABI_VERSION; }
+const char* dyf_act_dtype(void) { return DYF_ACT_NAME; }
+int dyf_nvtx_enable(int32_t on) { g_nvtx = on != 0; return 0; }
 const char* dyf_last_error(void) { return get_error(); }
 uint64_t dyf_launch_count(void) { return g_launches.load(); }
 
@@ -139,7 +158,13 @@ int dyf_net_forward_srcs(dyf_net* net, int32_t rows, const float* const* srcs, c
                          size_t workspace_bytes, void* stream) {
   if (!net || !srcs || !src_channels || !y || !workspace) { set_error("null argument"); return DYF_ERR_ARG; }
   if (int rc = require_device()) return rc;
-  return reinterpret_cast<Net*>(net)->forward(rows, srcs, src_channels, nsrc, time, y, drop, workspace, workspace_bytes,
+  RngCtx rng;
+  if (drop) {
+    if (drop->row_offset + (uint64_t)rows > 0xFFFFFFFFull) { set_error("row_offset out of range"); return DYF_ERR_ARG; }
+    rng.on = drop->mode == 1; rng.seed = drop->seed; rng.stream = drop->stream; rng.row_off = (uint32_t)drop->row_offset;
+  }
+  rng.group_rows = (uint32_t)rows;  // one logical call
+  return reinterpret_cast<Net*>(net)->forward(rows, srcs, src_channels, nsrc, time, y, rng, workspace, workspace_bytes,
                                               reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -212,18 +237,21 @@ int dyf_sampler_num_outputs(const dyf_sampler* s, int32_t* n_outputs, double* ke
 }
 
 int dyf_sampler_run(dyf_sampler* s, int32_t rows, const float* ic, const float* static_cond, float* preds,
-                    float* x0_hat_out, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream) {
+                    float* x0_hat_out, uint64_t seed, uint64_t row_offset, void* workspace, size_t workspace_bytes,
+                    void* stream) {
   if (!s || !ic || !preds || !workspace || rows <= 0) { set_error("bad argument"); return DYF_ERR_ARG; }
   if (int rc = require_device()) return rc;
-  return reinterpret_cast<Sampler*>(s)->run(rows, ic, static_cond, preds, x0_hat_out, seed, workspace, workspace_bytes,
-                                            reinterpret_cast<cudaStream_t>(stream));
+  return reinterpret_cast<Sampler*>(s)->run(rows, ic, static_cond, preds, x0_hat_out, seed, row_offset, workspace,
+                                            workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dyf_debug_dropout_mask(uint64_t seed, uint64_t stream, uint32_t site, float p, int64_t n_elems, uint8_t* mask,
                            void* stream_handle) {
   if (!mask || n_elems <= 0) { set_error("bad argument"); return DYF_ERR_ARG; }
   if (int rc = require_device()) return rc;
-  return launch_dropout_mask(make_drop(true, seed, stream, site, p), n_elems, mask,
+  RngCtx rng;
+  rng.on = true; rng.seed = seed; rng.stream = stream;
+  return launch_dropout_mask(make_drop(rng, site, p), n_elems, mask,
                              reinterpret_cast<cudaStream_t>(stream_handle));
 }
 

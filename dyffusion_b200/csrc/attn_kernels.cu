@@ -20,8 +20,8 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ bool keep1(const DropCfg& d, uint64_t elem) {
-  return (drop_keep_bits8(d, elem & ~7ull) >> (elem & 7)) & 1u;
+__device__ __forceinline__ bool keep1(const DropCfg& d, const DropRow& dr, uint64_t elem) {
+  return (drop_keep_bits8(d, dr, elem & ~7ull) >> (elem & 7)) & 1u;
 }
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(256) channel_ln_kernel(const ChannelLNParams p
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j];
   if (p.drop.thresh) {
-    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pix * p.C + c0);
+    const int r = (int)(pix / p.HW);
+    const uint32_t keep = drop_keep_bits8(p.drop, drop_row(p.drop, r, (uint64_t)p.HW * p.C),
+                                          (uint64_t)(pix - (long long)r * p.HW) * p.C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop.scale : 0.f;
   }
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256) channel_ln_wide_kernel(const ChannelLNPar
   const int lane = threadIdx.x & 31;
   const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pix >= p.M) return;
-  const __nv_bfloat16* x = p.x + (size_t)pix * p.C + lane * PER;
+  const act_t* x = p.x + (size_t)pix * p.C + lane * PER;
   float v[PER];
   unpack8(__ldg(reinterpret_cast<const uint4*>(x)), v);
   unpack8(__ldg(reinterpret_cast<const uint4*>(x) + 1), v + 8);
@@ -89,7 +91,9 @@ __global__ void __launch_bounds__(256) channel_ln_wide_kernel(const ChannelLNPar
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = (v[8 * half + j] - mean) * rstd * __ldg(p.g + lane * PER + 8 * half + j);
     if (p.drop.thresh) {
-      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pix * p.C + lane * PER + 8 * half);
+      const int r = (int)(pix / p.HW);
+      const uint32_t keep = drop_keep_bits8(p.drop, drop_row(p.drop, r, (uint64_t)p.HW * p.C),
+                                            (uint64_t)(pix - (long long)r * p.HW) * p.C + lane * PER + 8 * half);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = ((keep >> j) & 1u) ? o[j] * p.drop.scale : 0.f;
     }
@@ -111,12 +115,12 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const AttnParams p) {
   __shared__ float s_max[DH], s_den[8][DH];
   const int h = blockIdx.x, r = blockIdx.y;
   const int ld = 3 * p.heads * DH;
-  const __nv_bfloat16* kbase = p.qkv + (size_t)r * p.n * ld + p.heads * DH + h * DH;
-  const __nv_bfloat16* vbase = kbase + p.heads * DH;
+  const act_t* kbase = p.qkv + (size_t)r * p.n * ld + p.heads * DH + h * DH;
+  const act_t* vbase = kbase + p.heads * DH;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {  // ---- phase A
     float mx = -INFINITY;
-    for (int n = warp; n < p.n; n += 8) mx = fmaxf(mx, __bfloat162float(kbase[(size_t)n * ld + lane]));
+    for (int n = warp; n < p.n; n += 8) mx = fmaxf(mx, act2f(kbase[(size_t)n * ld + lane]));
     s_red[warp][lane] = mx;
     __syncthreads();
     if (warp == 0) {
@@ -250,11 +254,11 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   float* s_q = s_p + 8 * n * AQ;             // [8 warps][DH][AQ]  (scaled queries)
   const int h = blockIdx.x, r = blockIdx.y;
   const int ld = 3 * p.heads * DH;
-  const __nv_bfloat16* base = p.qkv + (size_t)r * n * ld + h * DH;
+  const act_t* base = p.qkv + (size_t)r * n * ld + h * DH;
   for (int i = threadIdx.x; i < n * DH; i += blockDim.x) {
     const int j = i / DH, d = i - j * DH;
-    s_kt[d * np + j] = __bfloat162float(base[(size_t)j * ld + p.heads * DH + d]);
-    s_v[j * DH + d] = __bfloat162float(base[(size_t)j * ld + 2 * p.heads * DH + d]);
+    s_kt[d * np + j] = act2f(base[(size_t)j * ld + p.heads * DH + d]);
+    s_v[j * DH + d] = act2f(base[(size_t)j * ld + 2 * p.heads * DH + d]);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     {  // the four queries, lane = channel
       float q[AQ];
 #pragma unroll
-      for (int t = 0; t < AQ; ++t) q[t] = i0 + t < n ? __bfloat162float(base[(size_t)(i0 + t) * ld + lane]) * scale : 0.f;
+      for (int t = 0; t < AQ; ++t) q[t] = i0 + t < n ? act2f(base[(size_t)(i0 + t) * ld + lane]) * scale : 0.f;
       qw[lane] = make_float4(q[0], q[1], q[2], q[3]);
     }
     __syncwarp();
@@ -290,11 +294,12 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       e.x = __expf(e.x - mx[0]); e.y = __expf(e.y - mx[1]); e.z = __expf(e.z - mx[2]); e.w = __expf(e.w - mx[3]);
       sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
       if (p.drop.thresh) {  // dropout on the probabilities (attention.py:59,70); element = ((row, head, query), key)
-        const uint64_t e0 = (((uint64_t)r * p.heads + h) * n + i0) * n + j;
-        e.x = keep1(p.drop, e0) ? e.x * p.drop.scale : 0.f;
-        e.y = keep1(p.drop, e0 + n) ? e.y * p.drop.scale : 0.f;
-        e.z = keep1(p.drop, e0 + 2 * (uint64_t)n) ? e.z * p.drop.scale : 0.f;
-        e.w = keep1(p.drop, e0 + 3 * (uint64_t)n) ? e.w * p.drop.scale : 0.f;
+        const DropRow dr = drop_row(p.drop, r, (((uint64_t)p.heads * n * n) + 7) & ~7ull);
+        const uint64_t e0 = ((uint64_t)h * n + i0) * n + j;
+        e.x = keep1(p.drop, dr, e0) ? e.x * p.drop.scale : 0.f;
+        e.y = keep1(p.drop, dr, e0 + n) ? e.y * p.drop.scale : 0.f;
+        e.z = keep1(p.drop, dr, e0 + 2 * (uint64_t)n) ? e.z * p.drop.scale : 0.f;
+        e.w = keep1(p.drop, dr, e0 + 3 * (uint64_t)n) ? e.w * p.drop.scale : 0.f;
       }
       pw[j] = e;
     }
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     }
 #pragma unroll
     for (int t = 0; t < AQ; ++t)
-      if (i0 + t < n) p.out[((size_t)r * n + i0 + t) * (p.heads * DH) + h * DH + lane] = __float2bfloat16_rn(o[t] * inv[t]);
+      if (i0 + t < n) p.out[((size_t)r * n + i0 + t) * (p.heads * DH) + h * DH + lane] = f2act(o[t] * inv[t]);
     __syncwarp();
   }
 }

@@ -13,7 +13,7 @@ struct PackParams {
   int src_rows;            // sources hold src_rows rows; output row r reads source row r % src_rows (batched calls)
   int rows, Hi, Wi, Ho, Wo, Cpad;
   int bilinear;            // 0 = same size copy, 1 = bilinear resize Hi x Wi -> Ho x Wo
-  __nv_bfloat16* out;
+  act_t* out;
   // "data+noise" forecaster conditioning (dyffusion.py:220-227): src[noise_src] <- w*src + (1-w)*N(0,1)
   int ones_channel;        // output channel set to 1.0 inside the image (carries a folded bias), -1 = none
   int s2d;                 // 1: space-to-depth packing -- output pixel (by, bx) holds the 2x2 block of the (resized)
@@ -21,6 +21,8 @@ struct PackParams {
   int noise_src;           // -1 = none
   float noise_w;
   uint64_t seed, stream;
+  const uint64_t* seed_ptr;  // device copy of the seed (CUDA-graph replays), or nullptr
+  uint32_t rng_rows, row_off;  // rows per logical call / global index of the first row (see DropCfg)
 };
 int launch_pack(const PackParams& p, cudaStream_t s);
 
@@ -30,7 +32,7 @@ struct StemParams {
   PackParams pk;           // sources / geometry (pk.out and pk.Cpad unused)
   const float* w;          // [Cout, Cin] fp32 (Conv2d 1x1 weight)
   const float* bias;       // [Cout]
-  __nv_bfloat16* out;      // [rows, Ho, Wo, Cout]
+  act_t* out;      // [rows, Ho, Wo, Cout]
   int Cin, Cout;
   DropCfg drop;
 };
@@ -38,25 +40,25 @@ int launch_stem(const StemParams& p, cudaStream_t s);
 
 // ---- x2 upsample (bilinear align_corners=False | nearest) of up to two bf16 NHWC sources into one concat buffer
 struct UpsampleParams {
-  const __nv_bfloat16* src[2];
+  const act_t* src[2];
   int C[2];      // channels taken from each source (multiples of 8); C[1] = 0 for a single source
   int ld[2];     // channel stride of each source
   int rows, H, W;  // source spatial size; output is [rows, 2H, 2W, C[0]+C[1]]
   int scale;     // 2 = upsample x2, 1 = plain concat copy
   int bilinear;  // 1 bilinear, 0 nearest
-  __nv_bfloat16* out;
+  act_t* out;
 };
 int launch_upsample(const UpsampleParams& p, cudaStream_t s);
 
 // ---- GroupNorm over bf16 NHWC (+ time scale/shift, activation, dropout, residual)
 struct GroupNormParams {
-  const __nv_bfloat16* x;   // [rows, HW, C] raw conv output (bias included)
-  __nv_bfloat16* y;         // [rows, HW, C]
+  const act_t* x;   // [rows, HW, C] raw conv output (bias included)
+  act_t* y;         // [rows, HW, C]
   const float* gamma;       // [C]
   const float* beta;        // [C]
   const float* tabA;        // [rows, C] (scale + 1) or nullptr
   const float* tabB;        // [rows, C] shift or nullptr
-  const __nv_bfloat16* res; // optional residual [rows, HW, res_ld], added last
+  const act_t* res; // optional residual [rows, HW, res_ld], added last
   float* stats;             // scratch, gn_scratch_floats(C, G) per row: [rows, G, 32 slabs, 2] per-slab partial sums
                             // (combined in fixed order) followed by the folded per-(row, channel) [rows, 2, C] (A, B)
   int slabs;                // set by the launcher
@@ -72,7 +74,7 @@ int gn_scratch_floats(int C, int G);  // floats of `stats` scratch per row
 // ---- Navier-Stokes readout: ConvTranspose2d(64->Cout, k4, s2, p1) on the Hs x Ws map followed by the bilinear
 //      resize (2Hs x 2Ws) -> (Ho x Wo); only the pixels the resize samples are ever computed.  fp32 NCHW output.
 struct ReadoutParams {
-  const __nv_bfloat16* x;  // [rows, Hs, Ws, 64]
+  const act_t* x;  // [rows, Hs, Ws, 64]
   const float* w;          // [64, Cout, 4, 4] (ConvTranspose2d layout)
   const float* bias;       // [Cout]
   float* y;                // [rows, Cout, Ho, Wo]
@@ -83,7 +85,7 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s);
 // 64 -> 16 * Cout (z[pixel][(ky*4+kx)*Cout + co] = sum_ci x[pixel][ci] * Wt[ci][co][ky][kx]); this kernel then gathers, for
 // every output pixel, the 2x2 bilinear corners x 2x2 valid taps from z and adds the bias.
 struct ReadoutGatherParams {
-  const __nv_bfloat16* z;  // [rows, Hs, Ws, 16 * Cout]
+  const act_t* z;  // [rows, Hs, Ws, 16 * Cout]
   const float* bias;       // [Cout]
   float* y;                // [rows, Cout, Ho, Wo]
   int rows, Hs, Ws, Cout, Ho, Wo;
@@ -96,17 +98,18 @@ int launch_k2s2_to_conv1x1(const float* w, float* out, int O, int C, cudaStream_
 
 // ---- attention blocks of the SST backbone (attn_kernels.cu)
 struct ChannelLNParams {
-  const __nv_bfloat16* x;  // [M, C]
-  __nv_bfloat16* y;        // [M, C]
+  const act_t* x;  // [M, C]
+  act_t* y;        // [M, C]
   const float* g;          // [C] gain
   long long M;
   int C;
+  int HW;                  // pixels per batch row (M = rows * HW)
   DropCfg drop;            // dropout on the qkv-projection input (attention.py:13)
 };
 int launch_channel_ln(const ChannelLNParams& p, cudaStream_t s);
 struct AttnParams {
-  const __nv_bfloat16* qkv;  // [rows, n, 3 * heads * 32]
-  __nv_bfloat16* out;        // [rows, n, heads * 32]
+  const act_t* qkv;  // [rows, n, 3 * heads * 32]
+  act_t* out;        // [rows, n, heads * 32]
   float* ctx;                // linear attention scratch [rows, heads, 32, 32]
   int rows, n, heads;
   DropCfg drop;              // dropout on the attention probabilities (full attention, attention.py:59,70)
@@ -141,11 +144,11 @@ int launch_time_tables(const TimeParams& p, cudaStream_t s);
 
 // ---- weight re-packing (finalize)
 // conv weight fp32 [O, I, KH, KW] -> bf16 [O, Kpad], k = (ky*KW+kx)*Cpad + c; optional weight standardisation
-int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
+int launch_repack_conv(const float* w, act_t* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
                        int standardize, cudaStream_t s);
 // composite weight of (1x1 conv Wi,bi : Cs -> Cm) followed by (conv W0 : Cm -> O, KHxKW): bf16 [O, Kpad] over Cs real
 // channels + one "ones" channel carrying bi (zero outside the image, like the padded 1x1 output)
-int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_bfloat16* out, int O, int Cm, int Cs,
+int launch_compose_conv(const float* w0, const float* wi, const float* bi, act_t* out, int O, int Cm, int Cs,
                         int KH, int KW, int Cpad, int Kpad, cudaStream_t s);
 // composite of (1x1 conv Wi,bi : Cs -> Cm) and (4x4/s2/p1 conv W0 : Cm -> O) expressed as a 3x3/s1/p1 conv over the
 // space-to-depth packed input (4 sub-positions x 16 slots = 64 channels): fp32 [O, 64, 3, 3]

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const size_t plane = (size_t)p.Hi * p.Wi;
-  __nv_bfloat16* o = p.out + (size_t)idx * p.Cpad;
+  act_t* o = p.out + (size_t)idx * p.Cpad;
   float v[8];
   int oc = 0;
   for (int s = 0; s < p.nsrc; ++s) {
@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
       } else {
         val = __ldg(pl + (size_t)oy * p.Wi + ox);
         if (s == p.noise_src) {
-          const uint64_t e = ((uint64_t)r * p.C[s] + c) * plane + (size_t)oy * p.Wi + ox;  // per OUTPUT row
-          Philox ph(p.seed);
-          uint4 rn = ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.stream, 0x4e4f4953u);
+          // per OUTPUT row: batch row r = (logical call r / rng_rows, row r % rng_rows + row_off of the un-sharded job)
+          const uint32_t jc = (uint32_t)r / p.rng_rows, rr = (uint32_t)r - jc * p.rng_rows + p.row_off;
+          const uint64_t e = ((uint64_t)rr * p.C[s] + c) * plane + (size_t)oy * p.Wi + ox;
+          Philox ph(rng_seed(p.seed, p.seed_ptr));
+          uint4 rn = ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.stream + jc, 0x4e4f4953u);
           val = p.noise_w * val + (1.f - p.noise_w) * gauss_from(rn.x, rn.y);
         }
       }
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     if (p.drop.thresh) {
-      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)pp * 64 + g * 8);
+      const uint32_t keep = drop_keep_bits8(p.drop, drop_row(p.drop, r, (uint64_t)k.Ho * k.Wo * 64),
+                                            (uint64_t)(oy * k.Wo + ox) * 64 + g * 8);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[g * 8 + e] = ((keep >> e) & 1u) ? acc[g * 8 + e] * p.drop.scale : 0.f;
     }
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
   const int c = ch << 3;
   const int s = c < p.C[0] ? 0 : 1;
   const int cs = s ? c - p.C[0] : c;
-  const __nv_bfloat16* src = p.src[s] + (size_t)r * p.H * p.W * p.ld[s] + cs;
+  const act_t* src = p.src[s] + (size_t)r * p.H * p.W * p.ld[s] + cs;
   uint4 outv;
   if (p.scale == 1) {
     outv = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)oy * p.W + ox) * p.ld[s]));
@@ -244,13 +247,13 @@ __global__ void __launch_bounds__(256) upsample2x_quad_kernel(const UpsamplePara
   const int s = c < p.C[0] ? 0 : 1;
   const int cs = s ? c - p.C[0] : c;
   const int ld = p.ld[s];
-  const __nv_bfloat16* src = p.src[s] + (size_t)r * p.H * p.W * ld + cs;
+  const act_t* src = p.src[s] + (size_t)r * p.H * p.W * ld + cs;
   const int ym = max(i - 1, 0), yp = min(i + 1, p.H - 1), xm = max(j - 1, 0), xp = min(j + 1, p.W - 1);
   const int ys[3] = {ym, i, yp};
   uint4 raw[3][3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const __nv_bfloat16* rowp = src + (size_t)ys[a] * p.W * ld;
+    const act_t* rowp = src + (size_t)ys[a] * p.W * ld;
     raw[a][0] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xm * ld));
     raw[a][1] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)j * ld));
     raw[a][2] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xp * ld));
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(256) upsample2x_quad_kernel(const UpsamplePara
   }
   float o[8];
   const int Wo = 2 * p.W;
-  __nv_bfloat16* out = p.out + (((size_t)r * 2 * p.H + 2 * i) * Wo + 2 * j) * Ct + c;
+  act_t* out = p.out + (((size_t)r * 2 * p.H + 2 * i) * Wo + 2 * j) * Ct + c;
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = 0.25f * h0[0][e] + 0.75f * h0[1][e];
   *reinterpret_cast<uint4*>(out) = pack8(o);
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const GroupNormPar
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, p.HW);
   float s1 = 0.f, s2 = 0.f;
-  const __nv_bfloat16* x = p.x + (size_t)r * p.HW * p.C + (ch << 3);
+  const act_t* x = p.x + (size_t)r * p.HW * p.C + (ch << 3);
   for (int px = p0 + threadIdx.x / chunks; px < p1; px += pstep) {
     float f[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)px * p.C)), f);
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormPar
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = apply_act(fmaf(f[j], av[j], bv[j]), p.act);
   if (p.drop.thresh) {
-    const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.C + c0);
+    const uint32_t keep = drop_keep_bits8(p.drop, drop_row(p.drop, r, (uint64_t)p.HW * p.C),
+                                          (uint64_t)(m - (long long)r * p.HW) * p.C + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop.scale : 0.f;
   }
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
   bilinear_coord(ox, W2, (float)W2 / (float)p.Wo, X[0], X[1], lx);
   const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
   float acc[RO_MAXC] = {0.f, 0.f, 0.f, 0.f};
-  const __nv_bfloat16* xr = p.x + (size_t)r * p.Hs * p.Ws * p.Cin + (sub << 3);
+  const act_t* xr = p.x + (size_t)r * p.Hs * p.Ws * p.Cin + (sub << 3);
   // 2 x 2 bilinear corners x 2 x 2 transposed-conv taps, all 16 combinations executed by every lane (no divergence):
   // invalid taps get weight 0 and a clamped address.
 #pragma unroll
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(const ReadoutGather
   bilinear_coord(oy, H2, (float)H2 / (float)p.Ho, Y[0], Y[1], ly);
   bilinear_coord(ox, W2, (float)W2 / (float)p.Wo, X[0], X[1], lx);
   const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
-  const __nv_bfloat16* zr = p.z + (size_t)r * p.Hs * p.Ws * ldz + co;
+  const act_t* zr = p.z + (size_t)r * p.Hs * p.Ws * ldz + co;
   float acc = 0.f;
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(const ReadoutGather
           const int ky = ((yy + 1) & 1) + 2 * dy, kx = ((xx + 1) & 1) + 2 * dx;
           const int iy = (yy + 1 - ky) >> 1, ix = (xx + 1 - kx) >> 1;
           if (iy >= 0 && iy < p.Hs && ix >= 0 && ix < p.Ws)
-            v += __bfloat162float(zr[((size_t)iy * p.Ws + ix) * ldz + (ky * 4 + kx) * p.Cout]);
+            v += act2f(zr[((size_t)iy * p.Ws + ix) * ldz + (ky * 4 + kx) * p.Cout]);
         }
       acc = fmaf(wy[a] * wx[b], v, acc);
     }
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(256) time_tables_kernel(const TimeParams p, in
 }
 
 // ------------------------------------------------------------------------------------------------ weight re-packing
-__global__ void __launch_bounds__(256) repack_conv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) repack_conv_kernel(const float* __restrict__ w, act_t* __restrict__ out,
                                                          int I, int KH, int KW, int Cpad, int Kpad, int standardize) {
   __shared__ float s_red[2][8];
   __shared__ float s_stat[2];
@@ -625,12 +629,12 @@ __global__ void __launch_bounds__(256) repack_conv_kernel(const float* __restric
       const int ky = tap / KW, kx = tap - ky * KW;
       v = (wo[((size_t)c * KH + ky) * KW + kx] - mean) * rstd;
     }
-    out[(size_t)o * Kpad + k] = __float2bfloat16_rn(v);
+    out[(size_t)o * Kpad + k] = f2act(v);
   }
 }
 
 __global__ void __launch_bounds__(256) compose_conv_kernel(const float* __restrict__ w0, const float* __restrict__ wi,
-                                                          const float* __restrict__ bi, __nv_bfloat16* __restrict__ out,
+                                                          const float* __restrict__ bi, act_t* __restrict__ out,
                                                           int Cm, int Cs, int taps, int Cpad, int Kpad) {
   const int o = blockIdx.x;
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(256) compose_conv_kernel(const float* __restri
         v = fmaf(a, ch < Cs ? wi[(size_t)m * Cs + ch] : bi[m], v);
       }
     }
-    out[(size_t)o * Kpad + k] = __float2bfloat16_rn(v);
+    out[(size_t)o * Kpad + k] = f2act(v);
   }
 }
 
@@ -695,7 +699,7 @@ __global__ void fill_kernel(float* p, float v, long long n) {
 __global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g * 8 >= n) return;
-  const uint32_t keep = d.thresh ? drop_keep_bits8(d, (uint64_t)g * 8) : 0xFFu;
+  const uint32_t keep = d.thresh ? drop_keep_bits8(d, drop_row(d, 0, 0), (uint64_t)g * 8) : 0xFFu;
   for (int j = 0; j < 8 && g * 8 + j < n; ++j) mask[g * 8 + j] = (keep >> j) & 1u;
 }
 
@@ -834,14 +838,14 @@ int launch_time_tables(const TimeParams& p, cudaStream_t s) {
   return 0;
 }
 
-int launch_repack_conv(const float* w, __nv_bfloat16* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
+int launch_repack_conv(const float* w, act_t* out, int O, int I, int KH, int KW, int Cpad, int Kpad,
                        int standardize, cudaStream_t s) {
   repack_conv_kernel<<<O, 256, 0, s>>>(w, out, I, KH, KW, Cpad, Kpad, standardize);
   DYF_LAUNCH_OK("repack_conv_kernel");
   return 0;
 }
 
-int launch_compose_conv(const float* w0, const float* wi, const float* bi, __nv_bfloat16* out, int O, int Cm, int Cs,
+int launch_compose_conv(const float* w0, const float* wi, const float* bi, act_t* out, int O, int Cm, int Cs,
                         int KH, int KW, int Cpad, int Kpad, cudaStream_t s) {
   compose_conv_kernel<<<O, 256, 0, s>>>(w0, wi, bi, out, Cm, Cs, KH * KW, Cpad, Kpad);
   DYF_LAUNCH_OK("compose_conv_kernel");

@@ -1,12 +1,32 @@
 // Shared device/host helpers of the dyffusion_b200 engine (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <string>
 
 namespace dyf {
+
+// ---------------------------------------------------------------- 16-bit storage type of activations and GEMM operands
+// fp16 by default: same tensor-core rate as bf16 (tcgen05 kind::f16 / mma.sync take either), but a 10-bit mantissa, i.e. 8x
+// less rounding per stored activation / operand -- what keeps 60-530 chained network calls of a sampling trajectory inside
+// the stated tolerance.  Conversions saturate (cvt.rn.satfinite), so the narrower exponent range cannot produce infinities;
+// accumulation, epilogues, statistics and the sampler state are fp32 either way.  -DDYF_ACT_BF16 builds the bf16 variant.
+#ifdef DYF_ACT_BF16
+typedef __nv_bfloat16 act_t;
+#define DYF_UMMA_FMT 1u                       /* tcgen05 instruction-descriptor a/b format: 1 = bf16 */
+#define DYF_MMA_T "bf16"
+#define DYF_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define DYF_ACT_NAME "bf16"
+#else
+typedef __half act_t;
+#define DYF_UMMA_FMT 0u                       /* 0 = f16 */
+#define DYF_MMA_T "f16"
+#define DYF_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define DYF_ACT_NAME "fp16"
+#endif
 
 // ---------------------------------------------------------------- error plumbing (thread-local message, C ABI)
 void set_error(const std::string& msg);
@@ -77,22 +97,39 @@ struct Philox {
   }
 };
 
-// Dropout of a run of 8 consecutive elements whose first flat element index is `elem0` (a multiple of 8).
-// keep-bit j uses 16 random bits; P(keep) = 1 - thresh/65536.  The mask is a pure function of
-// (seed, stream, site, element index), independent of the tiling of the kernel that applies it.
+// Dropout of a run of 8 consecutive elements (first element index a multiple of 8).  keep-bit j uses 16 random bits;
+// P(keep) = 1 - thresh/65536.  The mask is a pure function of (seed, logical call, site, GLOBAL row, element inside the
+// row): a batch row b of a launch sequence that carries several logical calls of `group_rows` rows each is row
+// r = b % group_rows of logical call j = b / group_rows (its own stream id, stream + j), and r is offset by `row_off`, the
+// index of the shard's first row in the un-sharded job.  So neither the tiling of a kernel, nor the batching of logical
+// calls, nor the number of ranks a job is split over changes which elements are dropped (a row-sharded
+// ensemble must not repeat masks across ranks).
 struct DropCfg {
   uint64_t seed;
+  const uint64_t* seed_ptr;            // when set, the seed is read from device memory (CUDA-graph replays draw new masks)
   uint32_t stream_lo, stream_hi_site;  // counter words 2,3
   uint32_t thresh;                     // 0 = dropout off
   float scale;                         // 1/(1-p)
+  uint32_t group_rows;                 // rows per logical call (>= 1)
+  uint32_t row_off;                    // global index of batch row 0 of every logical call
+};
+// what the sampler / a forward passes down to the layers: the RNG coordinates of one launch sequence
+struct RngCtx {
+  bool on = false;
+  uint64_t seed = 0, stream = 0;
+  const uint64_t* seed_ptr = nullptr;
+  uint32_t group_rows = 1, row_off = 0;
 };
 
-__host__ inline DropCfg make_drop(bool on, uint64_t seed, uint64_t stream, uint32_t site, float p) {
+__host__ inline DropCfg make_drop(const RngCtx& c, uint32_t site, float p) {
   DropCfg d;
-  d.seed = seed;
-  d.stream_lo = (uint32_t)stream;
-  d.stream_hi_site = ((uint32_t)(stream >> 32) & 0xFFFFu) | (site << 16);
-  if (!on || p <= 0.f) {
+  d.seed = c.seed;
+  d.seed_ptr = c.seed_ptr;
+  d.stream_lo = (uint32_t)c.stream;
+  d.stream_hi_site = ((uint32_t)(c.stream >> 32) & 0xFFFFu) | (site << 16);
+  d.group_rows = c.group_rows ? c.group_rows : 1;
+  d.row_off = c.row_off;
+  if (!c.on || p <= 0.f) {
     d.thresh = 0;
     d.scale = 1.f;
   } else {
@@ -103,10 +140,19 @@ __host__ inline DropCfg make_drop(bool on, uint64_t seed, uint64_t stream, uint3
   return d;
 }
 
-__device__ __forceinline__ uint32_t drop_keep_bits8(const DropCfg& d, uint64_t elem0) {
-  Philox ph(d.seed);
-  uint64_t g = elem0 >> 3;
-  uint4 r = ph((uint32_t)g, (uint32_t)(g >> 32), d.stream_lo, d.stream_hi_site);
+__device__ __forceinline__ uint64_t rng_seed(uint64_t seed, const uint64_t* seed_ptr) { return seed_ptr ? __ldg(seed_ptr) : seed; }
+
+// RNG coordinates of one batch row: stream word of its logical call and the element offset of its global row
+struct DropRow { uint32_t stream; uint64_t base; };
+__device__ __forceinline__ DropRow drop_row(const DropCfg& d, int batch_row, uint64_t elems_per_row) {
+  const uint32_t j = (uint32_t)batch_row / d.group_rows, r = (uint32_t)batch_row - j * d.group_rows;
+  return DropRow{d.stream_lo + j, (uint64_t)(r + d.row_off) * elems_per_row};
+}
+// keep bits of elements [e, e + 8) of that row (e a multiple of 8, elems_per_row a multiple of 8)
+__device__ __forceinline__ uint32_t drop_keep_bits8(const DropCfg& d, const DropRow& dr, uint64_t e) {
+  Philox ph(rng_seed(d.seed, d.seed_ptr));
+  const uint64_t g = (dr.base + e) >> 3;
+  uint4 r = ph((uint32_t)g, (uint32_t)(g >> 32), dr.stream, d.stream_hi_site);
   uint32_t w[4] = {r.x, r.y, r.z, r.w};
   uint32_t bits = 0;
 #pragma unroll
@@ -117,21 +163,41 @@ __device__ __forceinline__ uint32_t drop_keep_bits8(const DropCfg& d, uint64_t e
   return bits;
 }
 
-// ---------------------------------------------------------------- bf16 packing
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// ---------------------------------------------------------------- 16-bit packing
+#ifdef DYF_ACT_BF16
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+__host__ __device__ __forceinline__ act_t f2act(float v) { return __float2bfloat16_rn(v); }
+__host__ __device__ __forceinline__ float act2f(act_t v) { return __bfloat162float(v); }
+#else
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {  // round to nearest, saturate to +-65504
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+__device__ __forceinline__ act_t f2act(float v) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
+#endif
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  float2 a = unpack_act2(u.x), b = unpack_act2(u.y), c = unpack_act2(u.z), d = unpack_act2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  return make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

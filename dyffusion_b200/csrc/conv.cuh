@@ -7,16 +7,16 @@
 namespace dyf {
 
 struct ConvParams {
-  const __nv_bfloat16* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
-  const __nv_bfloat16* in2;  // optional second source [rows, Hi, Wi, Cin - Cin0]: the input is the channel concat
+  const act_t* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
+  const act_t* in2;  // optional second source [rows, Hi, Wi, Cin - Cin0]: the input is the channel concat
   int Cin0;                  //   [in | in2] without a concat buffer (tcgen05 TMA path only); 0 = single source
-  const __nv_bfloat16* w_umma;  // weights re-packed as UMMA stage tiles (conv_umma.cu) or nullptr
-  const __nv_bfloat16* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
+  const act_t* w_umma;  // weights re-packed as UMMA stage tiles (conv_umma.cu) or nullptr
+  const act_t* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
   void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32
   const float* tabA;         // [rows, Cout]  y = acc * A + B   (folded norm, conv bias, time scale/shift)
   const float* tabB;         // [rows, Cout]
   int tab_div;               // table row of batch row r is r / tab_div (rows of one logical call share a table)
-  const __nv_bfloat16* res;  // optional residual added after activation+dropout, [M, res_ld]
+  const act_t* res;  // optional residual added after activation+dropout, [M, res_ld]
   int rows, Hi, Wi, Cin;
   int Cin_real;              // un-padded input channels (FLOP accounting only)
   int Ho, Wo, Cout;
@@ -50,19 +50,20 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m,
       v[j] = (c0 + j < p.Cout) ? apply_act(fmaf(acc[j], __ldg(A + j), __ldg(B + j)), p.act) : 0.f;
   }
   if (p.drop.thresh) {
-    uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + c0);
+    uint32_t keep = drop_keep_bits8(p.drop, drop_row(p.drop, r, (uint64_t)HoWo * p.Cout),
+                                    (uint64_t)(m - (long long)r * HoWo) * p.Cout + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * p.drop.scale : 0.f;
   }
   if (p.res) {
-    const __nv_bfloat16* rp = p.res + (size_t)m * p.res_ld + c0;
+    const act_t* rp = p.res + (size_t)m * p.res_ld + c0;
     if (full) {
       float f[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += f[j];
     } else {
-      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) v[j] += __bfloat162float(rp[j]);
+      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) v[j] += act2f(rp[j]);
     }
   }
   if (p.out_fp32 == 2) {
@@ -78,11 +79,11 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m,
       for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[j] = v[j];
     }
   } else {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + c0;
+    act_t* o = reinterpret_cast<act_t*>(p.out) + (size_t)m * p.out_ld + p.out_coff + c0;
     if (full && ((p.out_ld | p.out_coff) & 7) == 0) {
       *reinterpret_cast<uint4*>(o) = pack8(v);
     } else {
-      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[j] = __float2bfloat16_rn(v[j]);
+      for (int j = 0; j < 8 && c0 + j < p.Cout; ++j) o[j] = f2act(v[j]);
     }
   }
 }
@@ -90,13 +91,13 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, long long m,
 // Fused decoder block: bilinear x2 upsample of the concatenated [src0 | src1] low-res maps + 3x3 / pad-1 conv, as a
 // composite conv Cin -> 4*Cout on the low-res grid with a depth-to-space epilogue (conv_up.cu).
 struct UpConvParams {
-  const __nv_bfloat16* src[2];  // low-res bf16 NHWC sources in concat order, [rows, H, W, ld[s]]
+  const act_t* src[2];  // low-res bf16 NHWC sources in concat order, [rows, H, W, ld[s]]
   int C[2], ld[2];              // channels taken from each source (multiples of 64; C[1] may be 0), channel strides
   int rows, H, W;               // low-res grid; the output is [rows, 2H, 2W, out_ld]
   int Cout;                     // output channels of the reference conv (multiple of 32); GEMM N = 4 * Cout
-  const __nv_bfloat16* w[9];    // composite weights as tcgen05 stage tiles: interior, first row, last row, first col,
+  const act_t* w[9];    // composite weights as tcgen05 stage tiles: interior, first row, last row, first col,
                                 // last col, corners (top-left, top-right, bottom-left, bottom-right)
-  __nv_bfloat16* out;
+  act_t* out;
   int out_ld;
   const float* tabA;            // [rows / tab_div, Cout] epilogue tables (as ConvParams)
   const float* tabB;
@@ -107,7 +108,7 @@ struct UpConvParams {
 bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W);
 size_t conv_up_weight_elems(int Cin, int Cout);
 #define DYF_UP_VARIANTS 9
-int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* scratch, cudaStream_t s);
+int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s);
 int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
 
 int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
@@ -117,7 +118,7 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream);
 bool conv_umma_eligible(const ConvParams& p);
 bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad);
 int umma_padded_cout(int Cout);
-int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
+int launch_repack_umma(const float* w, act_t* out, int O, int I, int k, int stride, int pad, int standardize,
                        cudaStream_t s);
 
 }  // namespace dyf

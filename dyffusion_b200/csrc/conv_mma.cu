@@ -21,7 +21,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." DYF_MMA_T "." DYF_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -32,8 +32,8 @@ __device__ __forceinline__ int swz(int row, int chunk) { return (chunk ^ ((row >
 template <int BN>
 __global__ void __launch_bounds__(THREADS) conv_mma_kernel(const ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sB = sA + STAGES * BM * BK;
+  act_t* sA = reinterpret_cast<act_t*>(smem_raw);
+  act_t* sB = sA + STAGES * BM * BK;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int warp_m = warp & 3, warp_n = warp >> 2;
@@ -62,14 +62,14 @@ __global__ void __launch_bounds__(THREADS) conv_mma_kernel(const ConvParams p) {
   while (kc >= p.Cin) { kc -= p.Cin; if (++kx == p.KW) { kx = 0; ++ky; } }
 
   auto load_stage = [&](int stage, int kb) {
-    __nv_bfloat16* a = sA + stage * BM * BK;
-    __nv_bfloat16* b = sB + stage * BN * BK;
+    act_t* a = sA + stage * BM * BK;
+    act_t* b = sB + stage * BN * BK;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int row = lrow + 64 * i;
       const bool v = mval[i] && ky < p.KH && (unsigned)(iy0[i] + ky) < (unsigned)p.Hi &&
                      (unsigned)(ix0[i] + kx) < (unsigned)p.Wi;
-      const __nv_bfloat16* src = v ? p.in + abase[i] + ((long long)ky * p.Wi + kx) * p.Cin + kc : p.in;
+      const act_t* src = v ? p.in + abase[i] + ((long long)ky * p.Wi + kx) * p.Cin + kc : p.in;
       cp_async16(smem_u32(a + row * BK + swz(row, seg)), src, v ? 16 : 0);
     }
 #pragma unroll
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(THREADS) conv_mma_kernel(const ConvParams p) {
       const int row = lrow + 64 * i;
       const int n = n0 + row;
       const bool v = n < p.Cout;
-      const __nv_bfloat16* src = v ? p.w + (size_t)n * p.Kpad + kb * BK + seg * 8 : p.w;
+      const act_t* src = v ? p.w + (size_t)n * p.Kpad + kb * BK + seg * 8 : p.w;
       cp_async16(smem_u32(b + row * BK + swz(row, seg)), src, v ? 16 : 0);
     }
     kc += BK;
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(THREADS) conv_mma_kernel(const ConvParams p) {
     __syncthreads();
     if (kb + STAGES - 1 < nkb) load_stage((kb + STAGES - 1) % STAGES, kb + STAGES - 1);
     cp_async_commit();
-    const __nv_bfloat16* a = sA + (kb % STAGES) * BM * BK;
-    const __nv_bfloat16* b = sB + (kb % STAGES) * BN * BK;
+    const act_t* a = sA + (kb % STAGES) * BM * BK;
+    const act_t* b = sB + (kb % STAGES) * BN * BK;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       uint32_t af[2][4];

@@ -114,7 +114,7 @@ struct __align__(8) Barriers {
 // is released, so a weight byte pulled from L2 feeds T x 128 GEMM rows; the patch of the 16 x 8T super-tile is one TMA
 // box and each tile's taps are start-address shifts inside it.  GT = filter taps per weight stage.
 template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
-__global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const __nv_bfloat16* __restrict__ wblob,
+__global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const act_t* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap,
                                                               const __grid_constant__ CUtensorMap tmap2,
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       int n_tile, row, oy0, ox0;
       decode(w, n_tile, row, oy0, ox0);
       const int acc = it & 1;
+      const DropRow dr = drop_row(p.drop, row, (uint64_t)p.Ho * p.Wo * p.Cout);
       const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
       const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
       const int oy = oy0 + (m_local >> 3);
@@ -228,8 +229,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       const int ox = ox0 + tile * TILE_W + (m_local & 7);
       const bool valid = oy < p.Ho && ox < p.Wo;
       const long long m = ((long long)row * p.Ho + oy) * p.Wo + ox;
-      __nv_bfloat16* const orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
-      const __nv_bfloat16* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
+      act_t* const orow = reinterpret_cast<act_t*>(p.out) + (size_t)m * p.out_ld + p.out_coff + n_tile * BN;
+      const act_t* const rrow = p.res ? p.res + (size_t)m * p.res_ld + n_tile * BN : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * T + tile) * BN;
 #pragma unroll 1
       for (int cg = cbeg; cg < cbeg + COLS; cg += 32) {
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
         if (thresh) {
 #pragma unroll
           for (int cs = 0; cs < 32; cs += 8) {
-            const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m * p.Cout + n_tile * BN + cg + cs);
+            const uint32_t keep = drop_keep_bits8(p.drop, dr, (uint64_t)(oy * p.Wo + ox) * p.Cout + n_tile * BN + cg + cs);
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[cs + j] = ((keep >> j) & 1u) ? y[cs + j] * dscale : 0.f;
           }
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     constexpr int PSTEP = PROD_THREADS / G::CPL;            // patch pixels covered per pass of the producer threads
     constexpr int ITERS = (G::PIX + PSTEP - 1) / PSTEP;
     const int g8 = ptid % G::CPL;                           // fixed 8-channel group of this thread
-    const __nv_bfloat16* const in_base = p.in;
+    const act_t* const in_base = p.in;
     int ca = 0;                                             // running chunk counter (A ring position)
     for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
       for (int w = w0; w < min(w0 + cw, num_work); ++w) {
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
         src_off[it] = so;
         dst_off[it] = dof;
       }
-      const __nv_bfloat16* const in_row = in_base + (size_t)row * p.Hi * p.Wi * p.Cin + g8 * 8;
+      const act_t* const in_row = in_base + (size_t)row * p.Hi * p.Wi * p.Cin + g8 * 8;
       for (int c = 0; c < nchunks; ++c, ++ca) {
         const int st = ca % AS;
         mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
     {
       const uint32_t leader = elect_one();
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (DYF_UMMA_FMT << 7) | (DYF_UMMA_FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
       // A descriptor high word: SBO | version 1 (bit 46) [| SWIZZLE_128B (bits 61-63) with SBO = one 128-B-pixel patch row]
       const uint32_t a_hi = S2TMA ? ((uint32_t)(((VW * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))  // SWIZZLE_128B
                             : TMA ? ((uint32_t)(((PWT * 128) >> 4) & 0x3FFF) | (1u << 14) | (2u << 29))
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
 }
 
 // weights fp32 [O, I, KH, KW] -> bf16 stage tiles [n_tile][chunk][tap][k8][n (BN)][8]: one contiguous blob per MMA stage
-__global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restrict__ w, act_t* __restrict__ out,
                                                          int O, int I, int BN, int taps, int ch, int standardize) {
   const int nchunks = I / ch, k8n = ch / 8;
   const long long total = (long long)((O + BN - 1) / BN * BN) * I * taps;
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
   const int chunk = (int)(r % nchunks); r /= nchunks;
   const int n_tile = (int)r;
   const int o = n_tile * BN + n, ci = chunk * ch + k8 * 8 + e;
-  if (o >= O) { out[idx] = __float2bfloat16_rn(0.f); return; }  // zero rows of a ragged last n-tile
+  if (o >= O) { out[idx] = f2act(0.f); return; }  // zero rows of a ragged last n-tile
   float v = w[((size_t)o * I + ci) * taps + tap];
   if (standardize) {  // WeightStandardizedConv2d (reference unet.py:32-40), recomputed per element (load-time only)
     const float* wo = w + (size_t)o * I * taps;
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(256) repack_umma_kernel(const float* __restric
     for (int i = 0; i < I * taps; ++i) { const float d = wo[i] - mean; s2 += d * d; }
     v = (v - mean) * rsqrtf(s2 / (I * taps) + 1e-5f);
   }
-  out[idx] = __float2bfloat16_rn(v);
+  out[idx] = f2act(v);
 }
 
 // Pipeline shapes that fill the 227 KB of one SM.  T = pixel tiles per work item (TMA mode), GT = taps per weight stage,
@@ -542,7 +543,7 @@ template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 1, 
 template <> struct Stages<S2K4, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };   // 148 KB (4 view stages) + 64 KB weights
 
 // Patch tensor map of a layer input, cached per (buffer, geometry): the workspace carving is stable across forwards.
-static int make_patch_tmap(const ConvParams& p, const __nv_bfloat16* src, int C, int pw, int ph, CUtensorMap* out) {
+static int make_patch_tmap(const ConvParams& p, const act_t* src, int C, int pw, int ph, CUtensorMap* out) {
   using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   const Key key{src, p.rows, p.Hi, p.Wi, C, pw, ph};
@@ -727,7 +728,7 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
 }
 
-int launch_repack_umma(const float* w, __nv_bfloat16* out, int O, int I, int k, int stride, int pad, int standardize,
+int launch_repack_umma(const float* w, act_t* out, int O, int I, int k, int stride, int pad, int standardize,
                        cudaStream_t s) {
   const int mode = mode_of(k, stride, pad);
   if (mode < 0) { set_error("repack_umma: unsupported geometry"); return -1; }

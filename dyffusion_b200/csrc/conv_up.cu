@@ -110,9 +110,11 @@ __device__ __forceinline__ void up_store(const UpConvParams& p, int img, int i, 
     m[g] = ((long long)img * (2 * p.H) + 2 * i + (cls >> 1)) * (2 * p.W) + 2 * j + (cls & 1);
   }
   if (p.drop.thresh) {
+    const uint64_t per_img = (uint64_t)(4 * p.H * p.W) * p.Cout;
+    const DropRow dr = drop_row(p.drop, img, per_img);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const uint32_t keep = drop_keep_bits8(p.drop, (uint64_t)m[g] * p.Cout + co[g]);
+      const uint32_t keep = drop_keep_bits8(p.drop, dr, (uint64_t)(m[g] - (long long)img * (4 * p.H * p.W)) * p.Cout + co[g]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) y[8 * g + e] = ((keep >> e) & 1u) ? y[8 * g + e] * p.drop.scale : 0.f;
     }
@@ -259,7 +261,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
   } else if (warp == EPI_WARPS + 1) {
     // =============================== MMA issuer ====================================================================
     const uint32_t leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (DYF_UMMA_FMT << 7) | (DYF_UMMA_FMT << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hi = (uint32_t)((G::SBO >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
     const uint32_t b_hi = (uint32_t)((128 >> 4) & 0x3FFF) | (1u << 14);
     const uint32_t a_lo0 = (1u << 16) | (smem_u32(sA) >> 4);
@@ -302,7 +304,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
       for (int w = first; w < num_work; w += gridDim.x) {
         int n_tile, img, i0, j0, side;
         decode(w, n_tile, img, i0, j0, side);
-        const __nv_bfloat16* wv = KIND == K_MAIN ? p.w[0] : KIND == K_ROW ? p.w[1 + side] : KIND == K_COL ? p.w[3 + side] : p.w[5 + side];
+        const act_t* wv = KIND == K_MAIN ? p.w[0] : KIND == K_ROW ? p.w[1 + side] : KIND == K_COL ? p.w[3 + side] : p.w[5 + side];
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wv) + (size_t)n_tile * nchunks * 9 * B_TAP;
         for (int c = 0; c < nchunks; ++c) {
 #pragma unroll 1
@@ -441,7 +443,7 @@ size_t conv_up_weight_elems(int Cin, int Cout) { return (size_t)4 * Cout * Cin *
 // w: conv weight fp32 [Cout, Cin, 3, 3].  Fills the nine composite variants as tcgen05 stage tiles: interior, first row,
 // last row, first column, last column, then the corners (top-left, top-right, bottom-left, bottom-right).
 // `scratch` must hold 4*Cout*Cin*9 floats.
-int launch_compose_up(const float* w, int Cout, int Cin, __nv_bfloat16* const* w_variants, float* scratch, cudaStream_t s) {
+int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s) {
   float ax[3][2][3][3];
   for (int k = 0; k < 3; ++k) axis_maps(k, ax[k]);
   const long long total = (long long)4 * Cout * Cin;

@@ -3,6 +3,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dyffusion_b200.h"
@@ -87,10 +88,11 @@ struct Net {
   long long packed_floats = 0, extra_floats = 0;
   size_t wq_elems = 0, wu_elems = 0;
   float* packed = nullptr;             // device: all fp32 params + folded vectors
-  __nv_bfloat16* wq = nullptr;         // device: packed bf16 conv weights
-  __nv_bfloat16* wq_umma = nullptr;    // device: weights of tcgen05-eligible layers as UMMA stage tiles
+  act_t* wq = nullptr;         // device: packed bf16 conv weights
+  act_t* wq_umma = nullptr;    // device: weights of tcgen05-eligible layers as UMMA stage tiles
   TimeLayer* d_time_layers = nullptr;  // device copy
   bool finalized = false;
+  uint64_t generation = 0;             // bumped whenever device buffers a captured graph may point to are released
   int Hin = 0, Win = 0;                // network grid (after the optional outer resize)
   // epilogue tables of time tuples seen before (the sampler's schedule is fixed, so every tuple recurs on every call):
   // key = the times of one forward's logical calls, value = device buffer [tabA | tabB | scratch]
@@ -113,7 +115,7 @@ struct Net {
   int finalize(cudaStream_t s);
   size_t workspace_bytes(int rows) const;
   int forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
-              const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s,
+              const RngCtx& rng, void* ws, size_t ws_bytes, cudaStream_t s,
               int noise_src = -1, float noise_w = 0.f, int src_rows = 0, int group_rows = 1,
               const float* host_times = nullptr);  // host copy of `time` (rows / group_rows values): enables the table cache
 };
@@ -126,10 +128,28 @@ struct Sampler {
   std::vector<double> out_keys;    // reference key number of every output slot
   std::vector<int> step_slot;      // schedule index -> output slot or -1
   std::vector<int> refine_slot;    // refinement index -> output slot
+  // CUDA-graph replay of the launch sequence (desc.cuda_graph): one entry per (rows, workspace, row offset)
+  struct GraphEntry {
+    int runs = 0;                    // plain runs seen for this key (the first one warms every lazily built cache)
+    bool failed = false;             // capture / instantiation failed once: stay on plain launches
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    uint64_t genF = 0, genI = 0;     // Net::generation at capture time
+    uint64_t kernels = 0;            // kernel launches inside the graph (for dyf_launch_count)
+  };
+  std::map<std::tuple<int, const void*, uint64_t>, GraphEntry> graphs;
+  ~Sampler();
   int plan();
   size_t workspace_bytes(int rows) const;
-  int run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, void* ws,
-          size_t ws_bytes, cudaStream_t s);
+  // the launch sequence of sample_loop on stream s (plain launches; capturable once the caches are warm)
+  int enqueue(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed,
+              const uint64_t* seed_dev, uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s);
+  int run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, uint64_t row_offset,
+          void* ws, size_t ws_bytes, cudaStream_t s);
 };
+
+bool profiling_enabled();          // abi.cu: per-launch event bracketing is on (incompatible with stream capture)
+uint64_t launch_counter();
+struct NvtxRange { bool on; NvtxRange(const char* what, int arch, int rows); ~NvtxRange(); };
 
 }  // namespace dyf

@@ -9,6 +9,10 @@
 namespace dyf {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static bool stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
 
 Net::~Net() {
   if (packed) cudaFree(packed);
@@ -21,6 +25,7 @@ Net::~Net() {
 void Net::clear_tab_cache() {
   for (auto& kv : tab_cache) cudaFree(kv.second);
   tab_cache.clear();
+  ++generation;  // captured graphs hold pointers into these buffers
 }
 
 int Net::add_param(const std::string& key, std::vector<int64_t> shape, bool ignored) {
@@ -528,13 +533,13 @@ int Net::set_param(const char* key, const void* data, const int64_t* shape, int 
 int Net::finalize(cudaStream_t s) {
   for (auto& p : params)
     if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
-  if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(__nv_bfloat16)));
-  if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(__nv_bfloat16)));
+  if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(act_t)));
+  if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(act_t)));
   for (auto& c : convs) {
     if (c.up_off[0] >= 0) {  // fused upsample + conv: composite weight variants (conv_up.cu)
       float* scratch = nullptr;
       DYF_CUDA_OK(cudaMalloc(&scratch, conv_up_weight_elems(c.Cin, c.Cout) * sizeof(float)));
-      __nv_bfloat16* variants[DYF_UP_VARIANTS];
+      act_t* variants[DYF_UP_VARIANTS];
       for (int v = 0; v < DYF_UP_VARIANTS; ++v) variants[v] = wq_umma + c.up_off[v];
       int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, scratch, s);
       if (ru) return ru;
@@ -615,13 +620,14 @@ size_t Net::workspace_bytes(int rows) const {
 }
 
 int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc, const float* time, float* y,
-                 const dyf_dropout* drop, void* ws, size_t ws_bytes, cudaStream_t s, int noise_src, float noise_w,
+                 const RngCtx& rng_in, void* ws, size_t ws_bytes, cudaStream_t s, int noise_src, float noise_w,
                  int src_rows, int group_rows, const float* host_times) {
   // `group_rows` consecutive rows share one time value (and hence one set of epilogue tables): `time` then holds
   // rows / group_rows entries (the sampler's logical calls); 1 = one time per row (the public forward)
   if (group_rows < 1 || rows % group_rows) { set_error("internal: bad group_rows"); return DYF_ERR_ARG; }
   const int tab_rows = rows / group_rows;
   if (!finalized) { set_error("net not finalized (call dyf_net_finalize after loading parameters)"); return DYF_ERR_STATE; }
+  NvtxRange nvtx("dyf.net.forward", d.arch, rows);
   if (rows <= 0) { set_error("rows must be positive"); return DYF_ERR_ARG; }
   if (ws_bytes < workspace_bytes(rows)) { set_error("workspace too small"); return DYF_ERR_ARG; }
   if (d.with_time_emb && !time && !host_times) { set_error("time is required (with_time_emb=True)"); return DYF_ERR_ARG; }
@@ -631,8 +637,8 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
     set_error("input/condition channels do not match num_input_channels + num_conditional_channels");
     return DYF_ERR_ARG;
   }
-  const bool drop_on = drop && drop->mode == 1;
-  const uint64_t seed = drop ? drop->seed : 0, stream_id = drop ? drop->stream : 0;
+  RngCtx rng = rng_in;
+  if (rng.group_rows == 0 || rng.group_rows > (uint32_t)rows) rng.group_rows = (uint32_t)rows;  // one logical call
 
   // ---- carve the workspace
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
@@ -644,9 +650,9 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
   base += align256((size_t)stats_floats_per_row * rows * sizeof(float));
   float* temb = reinterpret_cast<float*>(base);
   base += align256((size_t)time_dim * rows * sizeof(float));
-  std::vector<__nv_bfloat16*> bp(bufs.size());
+  std::vector<act_t*> bp(bufs.size());
   for (size_t i = 0; i < bufs.size(); ++i) {
-    bp[i] = reinterpret_cast<__nv_bfloat16*>(base);
+    bp[i] = reinterpret_cast<act_t*>(base);
     base += align256(bufs[i].row_bytes() * rows);
   }
 
@@ -659,6 +665,10 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
       std::vector<float> key(host_times, host_times + tab_rows);
       auto it = tab_cache.find(key);
       compute = it == tab_cache.end();
+      if (compute && stream_is_capturing(s)) {  // would allocate and copy from host memory inside a capture
+        set_error("internal: epilogue tables missing during graph capture");
+        return DYF_ERR_STATE;
+      }
       if (compute) {
         float* buf = nullptr;
         const size_t scratch = align256((size_t)(time_dim + 1) * tab_rows * sizeof(float));
@@ -705,7 +715,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.pk.bilinear = o.bilinear; p.pk.noise_src = -1;
         p.w = packed + params[c.w].off; p.bias = packed + params[c.b].off; p.out = bp[o.out];
         p.Cin = c.Cin; p.Cout = c.Cout;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         if (noise_src >= 0) { set_error("data+noise conditioning is not supported by the fused stem"); return DYF_ERR_UNSUPPORTED; }
         rc = launch_stem(p, s);
         break;
@@ -716,7 +726,8 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.nsrc = nsrc; p.src_rows = src_rows > 0 ? src_rows : rows; p.rows = rows; p.Hi = d.height; p.Wi = d.width;
         p.Ho = bufs[o.out].H; p.Wo = bufs[o.out].W; p.Cpad = bufs[o.out].C;
         p.bilinear = o.bilinear; p.out = bp[o.out];
-        p.noise_src = noise_src; p.noise_w = noise_w; p.seed = seed; p.stream = stream_id; p.ones_channel = o.ones_channel;
+        p.noise_src = noise_src; p.noise_w = noise_w; p.seed = rng.seed; p.stream = rng.stream; p.seed_ptr = rng.seed_ptr;
+        p.rng_rows = rng.group_rows; p.row_off = rng.row_off; p.ones_channel = o.ones_channel;
         p.s2d = o.aux;
         if (noise_src >= 0 && o.bilinear) { set_error("data+noise conditioning with an outer resize is unsupported"); return DYF_ERR_UNSUPPORTED; }
         rc = launch_pack(p, s);
@@ -736,7 +747,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tab_div = group_rows;
         p.act = o.act; p.M = (long long)rows * p.Ho * p.Wo;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         if (o.res >= 0) { p.res = bp[o.res]; p.res_ld = bufs[o.res].C; }
         if (o.out_mode == 2) { p.out = y; p.out_fp32 = 2; p.out_ld = c.Cout; }
         else { p.out = bp[o.out]; p.out_ld = bufs[o.out].C; p.out_coff = o.out_coff; }
@@ -762,7 +773,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tab_div = group_rows; p.act = o.act;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = launch_conv_up(p, s);
         break;
       }
@@ -788,7 +799,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.stats = stats + (size_t)n.stats_off * rows;
         p.rows = rows; p.HW = bufs[o.in0].H * bufs[o.in0].W; p.C = n.C; p.G = n.G; p.act = o.act; p.eps = 1e-5f;
         p.tab_div = group_rows;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = launch_groupnorm(p, s);
         break;
       }
@@ -811,8 +822,8 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         const LNLayer& l = lns[o.layer];
         ChannelLNParams p{};
         p.x = bp[o.in0]; p.y = bp[o.out]; p.g = packed + params[l.g].off;
-        p.M = (long long)rows * bufs[o.in0].H * bufs[o.in0].W; p.C = l.C;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.M = (long long)rows * bufs[o.in0].H * bufs[o.in0].W; p.C = l.C; p.HW = bufs[o.in0].H * bufs[o.in0].W;
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = launch_channel_ln(p, s);
         break;
       }
@@ -822,7 +833,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.qkv = bp[o.in0]; p.out = bp[o.out];
         p.ctx = o.aux > 0 ? reinterpret_cast<float*>(bp[o.aux]) : nullptr;
         p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.heads = 4;
-        p.drop = make_drop(drop_on, seed, stream_id, (uint32_t)o.site, o.drop_p);
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = o.type == OP_LINATTN ? launch_linear_attention(p, s) : launch_attention(p, s);
         break;
       }

@@ -65,21 +65,44 @@ static int batch_cap(const dyf_sampler_desc& d, int rows) {
   return std::max(2, cap / rows);
 }
 
+// workspace layout: [seed | staged ic | staged static | staged forecasts | staged x0_hat] (graph mode only) then the state
+// of the loop: x_s, x0_hat, interpolator outputs, network workspace
+static size_t stage_bytes(const Sampler& sm, int rows, size_t* off_ic, size_t* off_st, size_t* off_preds, size_t* off_x0) {
+  const size_t plane = (size_t)sm.F->d.height * sm.F->d.width * sizeof(float);
+  size_t o = 256;  // the seed
+  if (off_ic) *off_ic = o;
+  o += align256((size_t)rows * sm.d.window_channels * plane);
+  if (off_st) *off_st = o;
+  o += align256((size_t)rows * sm.d.static_channels * plane);
+  if (off_preds) *off_preds = o;
+  o += align256(sm.out_keys.size() * (size_t)rows * sm.d.channels * plane);
+  if (off_x0) *off_x0 = o;
+  o += align256((size_t)rows * sm.d.channels * plane);
+  return o;
+}
+
 size_t Sampler::workspace_bytes(int rows) const {
   const size_t plane = (size_t)F->d.height * F->d.width;
   const size_t state = align256((size_t)rows * d.channels * plane * sizeof(float));
   const int k = batch_cap(d, rows);
   size_t total = 2 * state;                                                    // x_s, x0_hat
   total += align256((size_t)k * rows * d.channels * plane * sizeof(float));     // interpolator outputs
-  total += align256((size_t)k * rows * sizeof(float));                          // time vector
   total += std::max(F->workspace_bytes(rows), I->workspace_bytes(k * rows));
+  total += d.cuda_graph ? stage_bytes(*this, rows, nullptr, nullptr, nullptr, nullptr) : 256;
   return total + 512;
 }
 
-int Sampler::run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, void* ws,
-                 size_t ws_bytes, cudaStream_t s) {
-  if (ws_bytes < workspace_bytes(rows)) { set_error("sampler workspace too small"); return DYF_ERR_ARG; }
-  if ((d.static_channels > 0) != (stat != nullptr)) { set_error("static_condition does not match static_channels"); return DYF_ERR_ARG; }
+Sampler::~Sampler() {
+  for (auto& kv : graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+}
+
+__global__ void store_seed_kernel(uint64_t* dst, uint64_t seed) { *dst = seed; }
+
+int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed,
+                     const uint64_t* seed_dev, uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s) {
   const int N = d.num_timesteps, n = (int)schedule.size(), C = d.channels;
   const size_t plane = (size_t)F->d.height * F->d.width;
   const size_t state_n = (size_t)rows * C * plane;
@@ -89,7 +112,6 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
   float* x_s = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
   float* x0_hat = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
   float* ybuf = reinterpret_cast<float*>(base); base += align256((size_t)kmax * state_n * sizeof(float));
-  base += align256((size_t)kmax * rows * sizeof(float));  // (time vector slot of the workspace layout; times now travel as host values)
   void* net_ws = base;
   const size_t net_ws_bytes = ws_bytes - (size_t)(base - reinterpret_cast<uint8_t*>(ws));
 
@@ -101,6 +123,8 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
   uint64_t call = 0;
   const bool f_cond_first = F->d.arch == DYF_ARCH_UNET_RESNET;  // unet.py:269 concatenates the condition first
   const bool i_cond_first = I->d.arch == DYF_ARCH_UNET_RESNET;
+  RngCtx rng;  // masks / noise are keyed by (seed, logical call, site, global row): see DropCfg
+  rng.seed = seed; rng.seed_ptr = seed_dev; rng.group_rows = (uint32_t)rows; rng.row_off = (uint32_t)row_offset;
 
   auto run_F = [&](int idx) -> int {  // predict_x_last (:205-239)
     const float* srcs[4];
@@ -118,8 +142,10 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     srcs[ns] = x_s; ch[ns++] = C;
     if (!f_cond_first) push_cond();
     const float th = (float)tF[idx];  // host copy of the time: the net keeps the epilogue tables of times it has seen
-    dyf_dropout dr{0, seed, call++};
-    return F->forward(rows, srcs, ch, ns, nullptr, x0_hat, &dr, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows, &th);
+    RngCtx r = rng;
+    r.on = d.forecaster_dropout != 0;  // experiment-level inference dropout reaches the forecaster too
+    r.stream = call++;
+    return F->forward(rows, srcs, ch, ns, nullptr, x0_hat, r, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows, &th);
   };
   // k logical interpolator calls at times t[0..k) sharing the inputs (ic, x0_hat); outputs land in ybuf[j]
   auto run_I = [&](const double* t, int k) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
@@ -131,9 +157,11 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
     srcs[ns] = x0_hat; ch[ns++] = C;
     if (!i_cond_first && stat) { srcs[ns] = stat; ch[ns++] = d.static_channels; }
     std::vector<float> th(t, t + k);  // host copy of the times: the net keeps the epilogue tables of tuples it has seen
-    dyf_dropout dr{d.enable_interpolator_dropout ? 1 : 0, seed, call};
+    RngCtx r = rng;
+    r.on = d.enable_interpolator_dropout != 0 || d.forecaster_dropout != 0;
+    r.stream = call;  // logical call j of the batch draws from stream call + j
     call += k;
-    return I->forward(k * rows, srcs, ch, ns, nullptr, ybuf, &dr, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows, th.data());
+    return I->forward(k * rows, srcs, ch, ns, nullptr, ybuf, r, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows, th.data());
   };
 
   for (int i = 0; i < n; ++i) {
@@ -185,6 +213,82 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
                                   state_n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   if (x0_out) DYF_CUDA_OK(cudaMemcpyAsync(x0_out, x0_hat, state_n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int Sampler::run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed,
+                 uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < workspace_bytes(rows)) { set_error("sampler workspace too small"); return DYF_ERR_ARG; }
+  if ((d.static_channels > 0) != (stat != nullptr)) { set_error("static_condition does not match static_channels"); return DYF_ERR_ARG; }
+  if (row_offset + (uint64_t)rows > 0xFFFFFFFFull) { set_error("row_offset out of range"); return DYF_ERR_ARG; }
+  NvtxRange nvtx("dyf.sampler.run", F->d.arch, rows);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  uint64_t* seed_dev = reinterpret_cast<uint64_t*>(base);
+  store_seed_kernel<<<1, 1, 0, s>>>(seed_dev, seed);
+  DYF_LAUNCH_OK("store_seed_kernel");
+  const size_t used = (size_t)(base - reinterpret_cast<uint8_t*>(ws));
+  if (!d.cuda_graph || profiling_enabled())
+    return enqueue(rows, ic, stat, preds, x0_out, seed, seed_dev, row_offset, base + 256, ws_bytes - used - 256, s);
+
+  // ---- graph mode: inputs / outputs staged through the workspace so that the captured pointers never change
+  size_t o_ic, o_st, o_preds, o_x0;
+  const size_t staged = stage_bytes(*this, rows, &o_ic, &o_st, &o_preds, &o_x0);
+  const size_t plane = (size_t)F->d.height * F->d.width * sizeof(float);
+  float* s_ic = reinterpret_cast<float*>(base + o_ic);
+  float* s_st = stat ? reinterpret_cast<float*>(base + o_st) : nullptr;
+  float* s_preds = reinterpret_cast<float*>(base + o_preds);
+  float* s_x0 = reinterpret_cast<float*>(base + o_x0);
+  DYF_CUDA_OK(cudaMemcpyAsync(s_ic, ic, (size_t)rows * d.window_channels * plane, cudaMemcpyDeviceToDevice, s));
+  if (stat) DYF_CUDA_OK(cudaMemcpyAsync(s_st, stat, (size_t)rows * d.static_channels * plane, cudaMemcpyDeviceToDevice, s));
+  void* loop_ws = base + staged;
+  const size_t loop_ws_bytes = ws_bytes - used - staged;
+
+  GraphEntry& g = graphs[std::make_tuple(rows, (const void*)base, row_offset)];
+  if (g.exec && (g.genF != F->generation || g.genI != I->generation)) {  // weights / tables were rebuilt: re-capture
+    cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
+    g = GraphEntry{};
+  }
+  int rc = 0;
+  if (g.exec) {
+    DYF_CUDA_OK(cudaGraphLaunch(g.exec, s));
+    count_launch((int)g.kernels);
+  } else if (g.failed || g.runs == 0) {
+    // first run of this key: plain launches (builds the epilogue tables, tensor maps and function attributes that the
+    // capture below must not have to create)
+    rc = enqueue(rows, s_ic, s_st, s_preds, s_x0, seed, seed_dev, row_offset, loop_ws, loop_ws_bytes, s);
+    if (rc) return rc;
+    ++g.runs;
+  } else {
+    const uint64_t l0 = launch_counter();
+    cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+    if (ce == cudaSuccess) {
+      rc = enqueue(rows, s_ic, s_st, s_preds, s_x0, seed, seed_dev, row_offset, loop_ws, loop_ws_bytes, s);
+      cudaGraph_t graph = nullptr;
+      ce = cudaStreamEndCapture(s, &graph);
+      if (rc == 0 && ce == cudaSuccess && graph) {
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce == cudaSuccess) {
+          g.exec = exec; g.graph = graph; g.genF = F->generation; g.genI = I->generation;
+          g.kernels = launch_counter() - l0;
+          DYF_CUDA_OK(cudaGraphLaunch(g.exec, s));
+        } else {
+          cudaGraphDestroy(graph);
+        }
+      } else if (graph) {
+        cudaGraphDestroy(graph);
+      }
+    }
+    if (!g.exec) {  // capture refused (e.g. a cache had to allocate): remember, clear the sticky error, launch plainly
+      cudaGetLastError();
+      g.failed = true;
+      rc = enqueue(rows, s_ic, s_st, s_preds, s_x0, seed, seed_dev, row_offset, loop_ws, loop_ws_bytes, s);
+      if (rc) return rc;
+    }
+  }
+  const size_t state = (size_t)rows * d.channels * plane;
+  DYF_CUDA_OK(cudaMemcpyAsync(preds, s_preds, out_keys.size() * state, cudaMemcpyDeviceToDevice, s));
+  if (x0_out) DYF_CUDA_OK(cudaMemcpyAsync(x0_out, s_x0, state, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

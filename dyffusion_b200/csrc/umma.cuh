@@ -146,7 +146,7 @@ inline EncodeTiledFn tensor_map_encoder() {
 }
 // 4-D tensor map over a bf16 NHWC activation tensor [rows, H, W, ld] (ld = channel stride, >= C): box = 64 channels x
 // bw x bh pixels x bn images, 128-B swizzle, zero fill out of bounds (= the convolution's zero padding).
-inline int make_nhwc_tmap(const __nv_bfloat16* base, int rows, int H, int W, int C, int ld, int bw, int bh, int bn,
+inline int make_nhwc_tmap(const act_t* base, int rows, int H, int W, int C, int ld, int bw, int bh, int bn,
                           CUtensorMap* out) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return -1;
@@ -154,19 +154,19 @@ inline int make_nhwc_tmap(const __nv_bfloat16* base, int rows, int H, int W, int
   cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t est[4] = {1, 1, 1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), gdim, gstr, box, est,
+  return fn(out, DYF_TMAP_DTYPE, 4, const_cast<act_t*>(base), gdim, gstr, box, est,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
 }
 
 // General 4-D bf16 tensor map: dims (innermost first, dims[0] = channels with unit stride), byte strides of dims 1..3,
 // box extents; 128-B swizzle, zero fill out of bounds.  Dimension order is free (e.g. (C, image, W, H)).
-inline int make_tmap4(const __nv_bfloat16* base, const cuuint64_t dims[4], const cuuint64_t strides[3], const cuuint32_t box[4],
+inline int make_tmap4(const act_t* base, const cuuint64_t dims[4], const cuuint64_t strides[3], const cuuint32_t box[4],
                       CUtensorMap* out, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return -1;
   cuuint32_t est[4] = {1, 1, 1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, est,
+  return fn(out, DYF_TMAP_DTYPE, 4, const_cast<act_t*>(base), dims, strides, box, est,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
 }

@@ -68,7 +68,8 @@ class DYffusion(BaseModel):
                  prediction_timesteps: Optional[Sequence[float]] = None,
                  enable_interpolator_dropout: Union[bool, str] = True,
                  use_cold_sampling_for_last_step: bool = False, log_every_t: Union[str, int] = None,
-                 sampling_timesteps: int = None, max_rows_per_call: int = 0, **kwargs):
+                 sampling_timesteps: int = None, max_rows_per_call: int = 0, cuda_graph: Optional[bool] = None,
+                 **kwargs):
         super().__init__(**kwargs)
         if model is None:
             raise ValueError("Arg ``model`` is missing... Please provide a backbone model for the diffusion model "
@@ -248,6 +249,21 @@ class DYffusion(BaseModel):
         steps = self.hparams.prediction_timesteps or list(self.dynamical_steps.values())
         return [i for i in steps if i < self.num_timesteps]
 
+    # ------------------------------------------------------------------ experiment-level inference dropout
+    def enable_inference_dropout(self):
+        """reference: `enable_inference_dropout(model)` switches EVERY nn.Dropout under the diffusion wrapper to train mode,
+        the forecaster's included (src/utilities/utils.py:560-567 via _base_model.py:163-169)."""
+        super().enable_inference_dropout()
+        for m in (self.model, getattr(self.interpolator, "model", None)):
+            if isinstance(m, BaseModel):
+                m.enable_inference_dropout()
+
+    def disable_inference_dropout(self):
+        super().disable_inference_dropout()
+        for m in (self.model, getattr(self.interpolator, "model", None)):
+            if isinstance(m, BaseModel):
+                m.disable_inference_dropout()
+
     def _native_ok(self, log_every_t) -> bool:
         ipol = getattr(self.interpolator, "model", None)
         sched = self.sampling_schedule
@@ -260,7 +276,7 @@ class DYffusion(BaseModel):
         refine = self._refine_times()
         key = (tuple(sched), tuple(refine), hp.forward_conditioning, hp.sampling_type, hp.time_encoding,
                bool(hp.use_cold_sampling_for_last_step), bool(self.enable_interpolator_dropout), static_channels,
-               window_channels)
+               window_channels, bool(self._inference_dropout))
         F, I = self.model.sync_engine(), self.interpolator.model.sync_engine()
         h = self._native_cache.get(key)
         if h is None:
@@ -272,21 +288,27 @@ class DYffusion(BaseModel):
                 use_cold_sampling_for_last_step=hp.use_cold_sampling_for_last_step, refine_times=refine,
                 enable_interpolator_dropout=self.enable_interpolator_dropout, channels=self.num_input_channels,
                 window_channels=window_channels, static_channels=static_channels,
-                interpolator_horizon=self.interpolator_horizon, max_rows_per_call=hp.get("max_rows_per_call", 0) or 0)
+                interpolator_horizon=self.interpolator_horizon, max_rows_per_call=hp.get("max_rows_per_call", 0) or 0,
+                forecaster_dropout=self._inference_dropout, cuda_graph=hp.get("cuda_graph"))
             self._native_cache[key] = h
         return h
 
     def sample_loop(self, initial_condition, static_condition: Optional[Tensor] = None,
-                    log_every_t: Optional[Union[str, int]] = None, num_predictions: int = None):
+                    log_every_t: Optional[Union[str, int]] = None, num_predictions: int = None, row_offset: int = 0):
+        """`row_offset` (not in the reference): index of row 0 of `initial_condition` in the un-sharded job.  Dropout masks
+        and the "data+noise" noise are functions of (seed, call, GLOBAL row), so `distributed.sample_sharded` -- every rank
+        holding the same torch seed, as under Lightning's seed_everything -- draws exactly what one rank would draw for the
+        whole job, and no two ranks repeat each other's ensemble members."""
         assert len(initial_condition.shape) == 4, f"condition.shape: {initial_condition.shape} (should be 4D)"
         log_every_t = log_every_t or self.hparams.log_every_t
         if not self._native_ok(log_every_t):
             return self._sample_loop_python(initial_condition, static_condition, log_every_t, num_predictions)
-        sampler = self._native_sampler(0 if static_condition is None else static_condition.shape[1],
-                                       initial_condition.shape[1])
+        with torch.cuda.device(initial_condition.device):
+            sampler = self._native_sampler(0 if static_condition is None else static_condition.shape[1],
+                                           initial_condition.shape[1])
         self._calls += 1
         seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * self._calls) & 0xFFFFFFFFFFFFFFFF
-        preds, x0_hat = sampler.run(initial_condition, static_condition, seed, want_x0=True)
+        preds, x0_hat = sampler.run(initial_condition, static_condition, seed, want_x0=True, row_offset=row_offset)
         out = {}
         for j, k in enumerate(sampler.keys):
             out[f"t{int(k) if float(k).is_integer() else k}_preds"] = preds[j]

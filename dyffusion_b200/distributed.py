@@ -3,7 +3,8 @@
 Rows (batch x ensemble members, member-major as produced by the reference's `get_ensemble_inputs`,
 src/experiment_types/_base_experiment.py:503-538) are independent through the whole sampling loop, so they are split
 contiguously over the ranks -- one process per GPU, no data-path collective -- and the per-rank forecasts are
-exchanged with ONE all-gather at the end.  Weights are replicated; each rank draws its own dropout stream."""
+exchanged with ONE all-gather at the end.  Weights are replicated; the dropout / noise streams are keyed by the global row
+index (`row_offset`), so the sharded job equals the un-sharded one bit for bit and no ensemble member is drawn twice."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
@@ -39,6 +40,19 @@ def gather_rows(local: torch.Tensor, rows_total: int, group=None) -> torch.Tenso
     return out[:, :rows_total]
 
 
+def _row_offset_kw(diffusion, first_row: int) -> dict:
+    """The engine drop-in keys its dropout / noise streams by the GLOBAL row (`sample_loop(row_offset=...)`): with the same
+    torch seed on every rank (Lightning's seed_everything) the sharded job draws what the un-sharded job would.  Foreign
+    diffusion modules (the reference's own) have no such argument: their ranks must be seeded differently by the caller."""
+    import inspect
+
+    fn = getattr(diffusion, "sample_loop", None)
+    try:
+        return {"row_offset": first_row} if fn is not None and "row_offset" in inspect.signature(fn).parameters else {}
+    except (TypeError, ValueError):
+        return {}
+
+
 def sample_sharded(diffusion, initial_condition: torch.Tensor, static_condition: Optional[torch.Tensor] = None,
                    group=None, **kwargs) -> Dict[str, torch.Tensor]:
     """`diffusion.sample` over this rank's shard of the rows + one all-gather; every rank returns the full dict.
@@ -51,7 +65,8 @@ def sample_sharded(diffusion, initial_condition: torch.Tensor, static_condition:
     keys: List[str]
     if e > b:
         out = diffusion.sample(initial_condition[b:e],
-                               static_condition=None if static_condition is None else static_condition[b:e], **kwargs)
+                               static_condition=None if static_condition is None else static_condition[b:e],
+                               **_row_offset_kw(diffusion, b), **kwargs)
         keys = list(out.keys())
         local = torch.stack([out[k] for k in keys])
     else:  # more ranks than rows: take the output structure from a one-row dry description

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DYF_LIB") or os.path.join(_HERE, "libdyffusion_b200.so")  # DYF_LIB: A/B builds of the same ABI
 
 ARCH_UNET_SIMPLE, ARCH_UNET_RESNET, ARCH_CONVNET = 0, 1, 2
+ABI_VERSION = 2
 
 
 class NetDesc(C.Structure):
@@ -31,7 +32,7 @@ class NetDesc(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64)]
+    _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64), ("row_offset", C.c_uint64)]
 
 
 class SamplerDesc(C.Structure):
@@ -42,7 +43,8 @@ class SamplerDesc(C.Structure):
         ("use_cold_sampling_for_last_step", C.c_int32), ("n_refine", C.c_int32),
         ("refine_times", C.POINTER(C.c_double)), ("enable_interpolator_dropout", C.c_int32),
         ("channels", C.c_int32), ("window_channels", C.c_int32), ("static_channels", C.c_int32),
-        ("interpolator_horizon", C.c_int32), ("max_rows_per_call", C.c_int32),
+        ("interpolator_horizon", C.c_int32), ("max_rows_per_call", C.c_int32), ("forecaster_dropout", C.c_int32),
+        ("cuda_graph", C.c_int32),
     ]
 
 
@@ -56,6 +58,8 @@ def _load() -> C.CDLL:
     sig = {
         "dyf_abi_version": (C.c_int, []),
         "dyf_last_error": (C.c_char_p, []),
+        "dyf_act_dtype": (C.c_char_p, []),
+        "dyf_nvtx_enable": (C.c_int, [i32]),
         "dyf_launch_count": (u64, []),
         "dyf_net_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(vp)]),
         "dyf_net_destroy": (None, [vp]),
@@ -72,7 +76,7 @@ def _load() -> C.CDLL:
         "dyf_sampler_destroy": (None, [vp]),
         "dyf_sampler_workspace_bytes": (C.c_int, [vp, i32, C.POINTER(sz)]),
         "dyf_sampler_num_outputs": (C.c_int, [vp, C.POINTER(i32), C.POINTER(C.c_double), i32]),
-        "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, vp, sz, vp]),
+        "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, u64, vp, sz, vp]),
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
         "dyf_ensemble_metrics_workspace_bytes": (C.c_int, [i32, C.c_int64, C.c_int64, C.POINTER(sz)]),
         "dyf_ensemble_metrics": (C.c_int, [vp, vp, i32, C.c_int64, C.c_int64, vp, vp, vp, sz, vp]),
@@ -91,13 +95,13 @@ def _load() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.dyf_abi_version() != 1:
+    if lib.dyf_abi_version() != ABI_VERSION:
         raise ImportError("libdyffusion_b200.so ABI version mismatch")
     return lib
 
 
 LIB = _load()
-EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_launch_count", "dyf_net_create", "dyf_net_destroy",
+EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_act_dtype", "dyf_nvtx_enable", "dyf_launch_count", "dyf_net_create", "dyf_net_destroy",
             "dyf_net_set_param", "dyf_net_finalize", "dyf_net_num_params", "dyf_net_param_key", "dyf_net_param_shape",
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
@@ -125,6 +129,15 @@ def _check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(LIB.dyf_launch_count())
+
+
+def act_dtype() -> str:
+    """Storage type of activations / tensor-core operands of the loaded library ("fp16" or "bf16")."""
+    return LIB.dyf_act_dtype().decode()
+
+
+def nvtx_enable(on: bool) -> None:
+    _check(LIB.dyf_nvtx_enable(int(bool(on))))
 
 
 def profile_enable(on: bool) -> None:
@@ -263,7 +276,8 @@ class NetHandle:
                 raise ValueError(f"time must have one entry per row ({rows}), got {time.numel()}")
         y = torch.empty((rows, d.out_channels, d.height, d.width), dtype=torch.float32, device=x.device)
         ws = WORKSPACE.get(self.workspace_bytes(rows), x.device)
-        dr = Dropout(1, dropout[0], dropout[1]) if dropout is not None else Dropout(0, 0, 0)
+        dr = Dropout(1, dropout[0], dropout[1], dropout[2] if len(dropout) > 2 else 0) if dropout is not None \
+            else Dropout(0, 0, 0, 0)
         with torch.cuda.device(x.device):
             _check(LIB.dyf_net_forward(
                 self._h, rows, C.c_void_p(x.data_ptr()), C.c_void_p(cond.data_ptr()) if cond is not None else None,
@@ -277,8 +291,12 @@ class SamplerHandle:
                  schedule: Sequence[float], tau: Sequence[float], time_forecaster: Sequence[float],
                  forward_conditioning: str, sampling_type: str, use_cold_sampling_for_last_step: bool,
                  refine_times: Sequence[float], enable_interpolator_dropout: bool, channels: int,
-                 window_channels: int, static_channels: int, interpolator_horizon: int, max_rows_per_call: int = 0):
+                 window_channels: int, static_channels: int, interpolator_horizon: int, max_rows_per_call: int = 0,
+                 forecaster_dropout: bool = False, cuda_graph: Optional[bool] = None):
         n = len(schedule)
+        if cuda_graph is None:  # default on; DYF_CUDA_GRAPH=0 keeps plain launches (A/B, debugging)
+            cuda_graph = os.environ.get("DYF_CUDA_GRAPH", "1") != "0"
+        self.cuda_graph = bool(cuda_graph)
         arr = lambda v: (C.c_double * max(1, len(v)))(*[float(x) for x in v])
         self._keep = (arr(schedule), arr(tau), arr(time_forecaster), arr(refine_times), forecaster, interpolator)
         fc = {"none": 0, "data": 1, "data+noise": 2}
@@ -290,7 +308,8 @@ class SamplerHandle:
         d = SamplerDesc(num_timesteps, n, self._keep[0], self._keep[1], self._keep[2], fc[forward_conditioning],
                         st[sampling_type], int(bool(use_cold_sampling_for_last_step)), len(refine_times),
                         self._keep[3], int(bool(enable_interpolator_dropout)), channels, window_channels,
-                        static_channels, interpolator_horizon, max_rows_per_call)
+                        static_channels, interpolator_horizon, max_rows_per_call, int(bool(forecaster_dropout)),
+                        int(bool(cuda_graph)))
         h = C.c_void_p()
         _check(LIB.dyf_sampler_create(forecaster.handle, interpolator.handle, C.byref(d), C.byref(h)))
         self._h = h
@@ -313,7 +332,7 @@ class SamplerHandle:
         return int(n.value)
 
     def run(self, ic: torch.Tensor, static: Optional[torch.Tensor], seed: int,
-            want_x0: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+            want_x0: bool = False, row_offset: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         ic = _require_cuda(ic, "initial_condition")
         rows = ic.shape[0]
         if tuple(ic.shape[1:]) != (self.window_channels, *self.hw):
@@ -329,7 +348,8 @@ class SamplerHandle:
             _check(LIB.dyf_sampler_run(
                 self._h, rows, C.c_void_p(ic.data_ptr()), C.c_void_p(static.data_ptr()) if static is not None else None,
                 C.c_void_p(preds.data_ptr()), C.c_void_p(x0.data_ptr()) if x0 is not None else None,
-                C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(_stream_ptr())))
+                C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint64(int(row_offset)), C.c_void_p(ws.data_ptr()), ws.numel(),
+                C.c_void_p(_stream_ptr())))
         return preds, x0
 
 

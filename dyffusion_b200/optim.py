@@ -147,8 +147,14 @@ class AdamW(torch.optim.Optimizer):
         return self._arenas[group].workspace[-1].sqrt()
 
     def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
-        """Accepts torch.optim.AdamW's state dict: moments are copied into the arenas, the views stay in place."""
+        """Accepts torch.optim.AdamW's state dict: moments are copied into the arenas, the views stay in place.
+        torch replaces every param_group by the saved one (keeping only `params`), and a group saved by torch.optim.AdamW has
+        no `max_grad_norm`: the clipping threshold of the live groups is kept in that case (it would silently vanish)."""
+        clips = [g.get("max_grad_norm", self.defaults.get("max_grad_norm")) for g in self.param_groups]
         super().load_state_dict(state_dict)
+        for g, clip in zip(self.param_groups, clips):
+            if "max_grad_norm" not in g:
+                g["max_grad_norm"] = clip
         for group, arena in zip(self.param_groups, self._arenas):
             steps = set()
             for i, p in enumerate(group["params"]):

@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
 #endif
 
-#define DYF_ABI_VERSION 1
+#define DYF_ABI_VERSION 2
 
 enum { DYF_OK = 0, DYF_ERR_ARG = -1, DYF_ERR_CUDA = -2, DYF_ERR_STATE = -3, DYF_ERR_UNSUPPORTED = -4 };
 
@@ -74,15 +74,21 @@ typedef struct dyf_sampler dyf_sampler;
 /* Dropout control of one forward.  mode 0 = off (the reference's eval mode), 1 = on with the engine's
  * counter-based Philox stream keyed by (seed, stream) (the reference's "inference dropout",
  * src/utilities/utils.py:560-574 + src/models/_base_model.py:148-161).  `stream` must differ between calls that
- * must draw independent masks. */
+ * must draw independent masks.  `row_offset` is the index of batch row 0 in the un-sharded job: masks (and the
+ * "data+noise" noise) are functions of the GLOBAL row, so a job split over several ranks draws exactly the masks of the
+ * same job on one rank (rows are the shard axis). */
 typedef struct dyf_dropout {
   int32_t mode;
   uint64_t seed;
   uint64_t stream;
+  uint64_t row_offset;
 } dyf_dropout;
 
 int dyf_abi_version(void);
 const char* dyf_last_error(void);
+/* Storage type of activations and tensor-core operands the library was built with: "fp16" (default) or "bf16"
+ * (accumulation, epilogues, statistics and the sampler state are fp32 either way). */
+const char* dyf_act_dtype(void);
 /* Number of CUDA kernels the engine has launched in this process (for bench.py's `gpu_launches`). */
 uint64_t dyf_launch_count(void);
 
@@ -155,6 +161,11 @@ typedef struct dyf_sampler_desc {
   int32_t static_channels;        /* channels of `static_condition` (0 = None) */
   int32_t interpolator_horizon;   /* for the 0 < t < horizon check (:484-486) */
   int32_t max_rows_per_call;      /* cap on rows per backbone launch when calls are batched (0 = default) */
+  int32_t forecaster_dropout;     /* dropout also ON in the forecaster: the reference's experiment-level
+                                     `enable_inference_dropout` (src/experiment_types/_base_experiment.py:288-299) */
+  int32_t cuda_graph;             /* 1: after one plain run per (rows, workspace, row_offset) the whole launch sequence of
+                                     `dyf_sampler_run` is captured into a CUDA graph and replayed (inputs / outputs are staged
+                                     through the workspace, the seed lives in device memory) */
 } dyf_sampler_desc;
 
 int dyf_sampler_create(dyf_net* forecaster, dyf_net* interpolator, const dyf_sampler_desc* desc, dyf_sampler** out);
@@ -166,9 +177,14 @@ int dyf_sampler_num_outputs(const dyf_sampler* s, int32_t* n_outputs, double* ke
 
 /* Replaces: `BaseDYffusion.sample_loop` / `sample` (src/diffusion/dyffusion.py:335-431).
  * ic: [rows, window_channels, H, W]; static_cond: [rows, static_channels, H, W] or NULL;
- * preds: [n_outputs, rows, C, H, W] fp32; x0_hat_out (optional): final forecaster output [rows, C, H, W]. */
+ * preds: [n_outputs, rows, C, H, W] fp32; x0_hat_out (optional): final forecaster output [rows, C, H, W].
+ * `row_offset`: index of row 0 in the un-sharded job (0 when the job is not sharded), see dyf_dropout. */
 int dyf_sampler_run(dyf_sampler* s, int32_t rows, const float* ic, const float* static_cond, float* preds,
-                    float* x0_hat_out, uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+                    float* x0_hat_out, uint64_t seed, uint64_t row_offset, void* workspace, size_t workspace_bytes,
+                    void* stream);
+/* NVTX ranges ("dyf.net.forward <arch> rows=..", "dyf.sampler.run") around every network call / sampler run, for
+ * nsys / ncu timelines (off by default; also switched on by the environment variable DYF_NVTX=1). */
+int dyf_nvtx_enable(int32_t on);
 
 /* Widening row SURVEY.md 8f-2 -- on-device ensemble evaluation.
  * Replaces: `evaluate_ensemble_prediction` (src/utilities/evaluation.py:10-80), `evaluate_ensemble_crps` (:83-97, i.e.

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     nm = subprocess.run(["nm", "-D", "--defined-only", E.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (dyf_[a-z_0-9]+)", nm))
     assert declared <= exported, declared - exported
-    assert E.LIB.dyf_abi_version() == 1
+    assert E.LIB.dyf_abi_version() == E.ABI_VERSION == 2
     assert E.launch_count() >= 0
 
 
