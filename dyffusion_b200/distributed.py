@@ -53,6 +53,16 @@ def _row_offset_kw(diffusion, first_row: int) -> dict:
         return {}
 
 
+def _stacked(out: Dict[str, torch.Tensor], keys: List[str]) -> torch.Tensor:
+    """[K, rows, ...] of the forecasts: the engine's sampler returns them as views of one such tensor -- use it as it is."""
+    first = out[keys[0]]
+    base = first._base
+    if (base is not None and base.dim() == first.dim() + 1 and base.shape[0] == len(keys) and base.is_contiguous() and
+            all(out[k].data_ptr() == base[i].data_ptr() and out[k].shape == base[i].shape for i, k in enumerate(keys))):
+        return base
+    return torch.stack([out[k] for k in keys])
+
+
 def sample_sharded(diffusion, initial_condition: torch.Tensor, static_condition: Optional[torch.Tensor] = None,
                    group=None, **kwargs) -> Dict[str, torch.Tensor]:
     """`diffusion.sample` over this rank's shard of the rows + one all-gather; every rank returns the full dict.
@@ -68,7 +78,7 @@ def sample_sharded(diffusion, initial_condition: torch.Tensor, static_condition:
                                static_condition=None if static_condition is None else static_condition[b:e],
                                **_row_offset_kw(diffusion, b), **kwargs)
         keys = list(out.keys())
-        local = torch.stack([out[k] for k in keys])
+        local = _stacked(out, keys)
     else:  # more ranks than rows: take the output structure from a one-row dry description
         keys, local = [], None
     # all ranks must agree on the keys; rank 0 always owns rows

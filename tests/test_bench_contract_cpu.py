@@ -24,7 +24,15 @@ def test_reference_arm_prints_the_contract_line():
     assert e2e == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sys.path.insert(0, ROOT)
     import bench
-    assert d["config"]["workload"] == bench.workload(bench.ROWS) and "BASELINE configs[1]" in d["config"]["workload"]
+    assert d["config"]["workload"] == bench.workload("ns", 64, "weak", 1) and "BASELINE configs[1]" in d["config"]["workload"]
+
+
+def test_reference_arm_covers_the_other_shipped_configurations():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "spring", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert "spring-mesh 10x10 h=134" in d["metric"] and "configs[3]" in d["config"]["workload"] and d["value"] > 0
 
 
 def test_reference_arm_is_silent_on_other_ranks():
