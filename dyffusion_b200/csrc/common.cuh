@@ -36,7 +36,7 @@ void count_launch(int n = 1);
 // Optional per-launch CUDA-event bracketing (bench.py's roofline measurement): when enabled, every kernel launch
 // is timed on its own stream and accumulated per kernel class.
 enum KernelClass : int { KC_CONV_MMA = 0, KC_CONV_UMMA, KC_PACK, KC_UPSAMPLE, KC_GROUPNORM, KC_READOUT, KC_TIME,
-                         KC_ELEMENTWISE, KC_ATTENTION, KC_CONV_UP, KC_COUNT };
+                         KC_ELEMENTWISE, KC_ATTENTION, KC_CONV_UP, KC_CONV_FLAT, KC_COUNT };
 struct ProfScope {
   cudaStream_t s;
   int idx;
@@ -66,12 +66,22 @@ struct ProfScope {
 // ---------------------------------------------------------------- activations (fp32 math)
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SILU = 3, ACT_GELU = 4 };
 
+// erf to 1.5e-7 absolute (Abramowitz-Stegun 7.1.26): one reciprocal, one exp2 and five FMAs instead of erff's ~40
+// instructions -- the GELU epilogue of the spring-mesh layers is issue-bound.  nn.GELU() is the exact erf form; the
+// difference (<= 1e-7 |x|) is three orders below the fp16 rounding of the stored activation.
+__device__ __forceinline__ float erf_fast(float z) {
+  const float az = fabsf(z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return copysignf(1.f - poly * __expf(-az * az), z);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(v, 0.f);
     case ACT_LEAKY: return v > 0.f ? v : 0.2f * v;                       // RELU_LEAK = 0.2 (unet_simple.py:10)
     case ACT_SILU: return v / (1.f + __expf(-v));
-    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() = exact erf form
+    case ACT_GELU: return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));  // nn.GELU() = erf form
     default: return v;
   }
 }

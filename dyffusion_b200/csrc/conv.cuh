@@ -111,6 +111,48 @@ size_t conv_up_weight_elems(int Cin, int Cout);
 int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s);
 int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
 
+// ---- spring-mesh layers on flat padded rasters (conv_flat.cu)
+struct FlatGeo { int p, S, PI, PC; };  // halo width, row stride, positions per image, positions per logical call
+FlatGeo flat_geo(int H, int W, int k, int G);      // raster read by a k x k layer, G rows per logical call
+bool conv_flat_shape_ok(int H, int W, int k, int Cout);
+struct FlatConvParams {
+  const act_t* in;        // raster of this layer [calls * PC_in][Cin]
+  const act_t* w;         // stage tiles [chunk][tap][k8][64][8], `wrep` identical copies `wrep_stride` elements apart
+  int wrep;
+  long long wrep_stride;
+  act_t* out;             // raster of the next layer [calls * PC_out][64] (only valid pixels are written)
+  const act_t* res;       // residual (= in when Cin == 64) or nullptr
+  const float* tabA;      // [calls][64] epilogue tables: y = act(acc * A + B)
+  const float* tabB;
+  int H, W, G, calls;     // image grid, rows per logical call, logical calls in this launch
+  int S_in, PI_in, PC_in, S_out, PI_out, PC_out;
+  int Cin;                // raster channels (multiple of 64)
+  int ntaps, halo;        // filter taps as position shifts, max |shift|
+  int shift[81];
+  int act;
+  double flops_k;         // reference K of the layer (Cin_real * k * k) for FLOP accounting
+  // 1x1 head fused into the epilogue of the last layer (simple_conv_net.py:102): y[row][oc][H][W] = head_w[oc] . act + head_b
+  const float* head_w;    // [head_oc][64] fp32, or nullptr
+  const float* head_b;
+  float* head_out;        // fp32 NCHW network output; when set, `out` is not written
+  int head_oc;            // <= 8
+  DropCfg drop;
+};
+struct FlatPackParams {
+  const float* slot_ptr[16];      // channel plane of row 0 for every channel slot (concat order over the fp32 NCHW sources)
+  long long slot_rstride[16];     // floats between consecutive rows of that source
+  int n_slots, src_rows;
+  int rows, H, W, k, G;   // k = kernel size of the first layer (horizontal taps packed into the channel axis)
+  int CP, Cflat;          // channel slots per horizontal tap, raster channels = round_up(k * CP, 64)
+  int S, PI, PC;
+  act_t* out;
+};
+int launch_pack_flat(const FlatPackParams& p, cudaStream_t s);
+int launch_conv_flat(const FlatConvParams& p, cudaStream_t stream);
+int flat_weight_replicas();  // copies of every flat layer's filter kept in global memory (DYF_FLAT_WREP, default 8)
+int launch_repack_flat(const float* w, act_t* out, int Cin, int k, cudaStream_t s);
+int launch_repack_flat_first(const float* w, act_t* out, int Cin, int k, int CP, int Cflat, cudaStream_t s);
+
 int launch_conv_mma(const ConvParams& p, cudaStream_t stream);
 // Returns 1 if the tcgen05 path took the layer, 0 if the shape is not eligible (caller falls back to the mma
 // pipeline), <0 on error.

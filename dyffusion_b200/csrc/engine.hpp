@@ -35,6 +35,9 @@ struct ConvLayer {
   int comp_wi = -1, comp_bi = -1, comp_cm = 0;  // composite layer: preceded by a folded 1x1 conv (weights, bias, width)
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
   long long up_off[DYF_UP_VARIANTS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // fused upsample+conv: composite variants in wq_umma
+  long long flat_off = -1, flat_elems = 0;    // flat-raster path (conv_flat.cu): stage tiles in wq_umma (x replicas)
+  int flat_first = 0;                         // first layer: horizontal taps folded into the channel axis (CP slots per tap)
+  int flat_cp = 0, flat_cin = 0;              // channel slots per horizontal tap, raster channels read by the layer
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
   int table = -1;                             // index into Net::time_layers
 };
@@ -46,7 +49,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN, OP_FLAT_PACK, OP_FLAT_CONV };
 constexpr int BUF_NONE = -1;
 
 struct Op {
@@ -68,7 +71,8 @@ struct Buf {
   size_t row_bytes() const { return (size_t)H * W * C * 2; }
 };
 
-struct LNLayer { int g = -1; int C = 0; };  // channel LayerNorm (gain only) in front of an attention block
+struct LNLayer { int g = -1; int C = 0; };
+struct FlatBuf { int k = 1, C = 64; };  // raster read by a k x k layer, C channels per position (conv_flat.cu)  // channel LayerNorm (gain only) in front of an attention block
 
 struct Net {
   dyf_net_desc d{};
@@ -79,6 +83,12 @@ struct Net {
   std::vector<LNLayer> lns;
   std::vector<Op> ops;
   std::vector<Buf> bufs;
+  std::vector<FlatBuf> flats;          // rasters of the flat path; device memory below, zeroed when (re)allocated
+  act_t* flat_mem = nullptr;
+  size_t flat_bytes = 0;
+  int flat_G = 0, flat_calls = 0;      // geometry the rasters are currently laid out (and zeroed) for
+  std::vector<size_t> flat_offs;
+  int ensure_flat(int G, int calls, cudaStream_t s);
   std::vector<TimeLayer> time_layers;
   int t_w1 = -1, t_b1 = -1, t_w2 = -1, t_b2 = -1;
   int ro_w = -1, ro_b = -1;  // readout params

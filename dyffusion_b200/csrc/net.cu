@@ -19,6 +19,7 @@ Net::~Net() {
   if (wq) cudaFree(wq);
   if (wq_umma) cudaFree(wq_umma);
   if (d_time_layers) cudaFree(d_time_layers);
+  if (flat_mem) cudaFree(flat_mem);
   clear_tab_cache();
 }
 
@@ -316,6 +317,53 @@ int Net::build_convnet() {
   Hin = d.height; Win = d.width;
   if (dim % 8) { set_error("SimpleConvNet: dim must be a multiple of 8"); return DYF_ERR_UNSUPPORTED; }
   int site = 1;
+  // Flat-raster tensor-core path (conv_flat.cu): every layer is dim -> 64 on a grid small enough for a <= 64-position halo
+  bool flat = dim == 64 && d.n_kernels >= 1 && !getenv("DYF_DISABLE_FLAT") && !getenv("DYF_DISABLE_UMMA");
+  for (int i = 0; flat && i < d.n_kernels; ++i) flat = conv_flat_shape_ok(Hin, Win, d.kernel_sizes[i], dim);
+  if (flat) {
+    const int k0 = d.kernel_sizes[0], cp = round_up(cin, 8), cflat = round_up(k0 * cp, 64);
+    flat = cin <= 16 && cflat <= 256 && (k0 - 1) / 2 * (Win + (k0 - 1) / 2) <= 64;
+    if (flat) {
+      FlatBuf fb; fb.k = k0; fb.C = cflat;
+      flats.push_back(fb);
+      Op pk{}; pk.type = OP_FLAT_PACK; pk.out = 0;
+      ops.push_back(pk);
+      int C = cin, last = BUF_NONE;
+      for (int i = 0; i < d.n_kernels; ++i) {
+        const std::string p = "convs." + std::to_string(i);
+        const int k = d.kernel_sizes[i];
+        int li = add_conv(p + ".conv", C, dim, k, 1, (k - 1) / 2);
+        attach_bn(convs[li], p + ".norm");
+        attach_time(convs[li].tw, convs[li].tb, p + ".time_mlp.1", dim);
+        ConvLayer& c = convs[li];
+        c.flat_first = i == 0; c.flat_cp = cp; c.flat_cin = i == 0 ? cflat : dim;
+        c.flat_off = (long long)wu_elems;
+        c.flat_elems = (long long)(i == 0 ? k : k * k) * c.flat_cin * 64;
+        wu_elems += (size_t)c.flat_elems * flat_weight_replicas();
+        Op o{}; o.type = OP_FLAT_CONV; o.in0 = i; o.layer = li; o.act = ACT_GELU; o.drop_p = d.dropout; o.site = site++;
+        if (d.residual && C == dim) o.res = i;  // residual only when C_in == C_out (:31, :53-54): the layer's own input raster
+        if (i + 1 < d.n_kernels) {
+          FlatBuf nb; nb.k = d.kernel_sizes[i + 1]; nb.C = dim;
+          flats.push_back(nb);
+          o.out = i + 1;
+        } else {
+          last = add_buf(Hin, Win, dim);  // plain NHWC for the 1x1 head (unused when the head is fused into this layer)
+          o.out = last; o.aux = 1;
+        }
+        ops.push_back(o);
+        C = dim;
+      }
+      int hl = add_conv("head", dim, d.out_channels, 1, 1, 0);
+      if (d.out_channels <= 8 && !getenv("DYF_FLAT_NO_HEAD_FUSION")) {
+        ops.back().aux = 2;          // last conv layer computes the head in its epilogue
+        ops.back().c0 = hl;
+      } else {
+        Op h{}; h.type = OP_CONV; h.in0 = last; h.layer = hl; h.out_mode = 2;
+        ops.push_back(h);
+      }
+      return 0;
+    }
+  }
   int x = add_buf(Hin, Win, round_up(cin, 8));
   Op pk{}; pk.type = OP_PACK; pk.out = x; pk.bilinear = 0;
   ops.push_back(pk);
@@ -546,6 +594,14 @@ int Net::finalize(cudaStream_t s) {
       DYF_CUDA_OK(cudaStreamSynchronize(s));
       DYF_CUDA_OK(cudaFree(scratch));
     }
+    if (c.flat_off >= 0) {  // flat-raster stage tiles (conv_flat.cu)
+      int rf = c.flat_first ? launch_repack_flat_first(packed + params[c.w].off, wq_umma + c.flat_off, c.Cin, c.KH, c.flat_cp, c.flat_cin, s)
+                            : launch_repack_flat(packed + params[c.w].off, wq_umma + c.flat_off, c.Cin, c.KH, s);
+      if (rf) return rf;
+      for (int r = 1; r < flat_weight_replicas(); ++r)
+        DYF_CUDA_OK(cudaMemcpyAsync(wq_umma + c.flat_off + (size_t)r * c.flat_elems, wq_umma + c.flat_off,
+                                    (size_t)c.flat_elems * sizeof(act_t), cudaMemcpyDeviceToDevice, s));
+    }
     if (c.convt_z) {  // ConvTranspose2d weight re-laid out as a 1x1 conv weight [16 * Cout_t, Cin] (fp32 staging)
       float* wz = nullptr;
       DYF_CUDA_OK(cudaMalloc(&wz, (size_t)c.Cout * c.Cin * sizeof(float)));
@@ -609,6 +665,33 @@ int Net::finalize(cudaStream_t s) {
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Rasters of the flat path: net-owned, laid out for (G rows per logical call, `calls` logical calls) and zeroed whenever that
+// geometry changes -- kernels only ever write valid pixels, so the zero gaps (= every layer's padding) persist between calls.
+int Net::ensure_flat(int G, int calls, cudaStream_t s) {
+  if (flats.empty() || (G == flat_G && calls <= flat_calls)) return 0;
+  if (stream_is_capturing(s)) { set_error("internal: raster allocation during graph capture"); return DYF_ERR_STATE; }
+  const int cap = G == flat_G ? std::max(calls, flat_calls) : calls;
+  std::vector<size_t> offs(flats.size());
+  size_t total = 0;
+  for (size_t i = 0; i < flats.size(); ++i) {
+    offs[i] = total;
+    const FlatGeo g = flat_geo(d.height, d.width, flats[i].k, G);
+    total += ((size_t)cap * g.PC * flats[i].C * sizeof(act_t) + 1023) & ~(size_t)1023;
+  }
+  if (total > flat_bytes) {
+    DYF_CUDA_OK(cudaStreamSynchronize(s));  // earlier launches may still read the old rasters
+    if (flat_mem) DYF_CUDA_OK(cudaFree(flat_mem));
+    flat_mem = nullptr; flat_bytes = 0;
+    DYF_CUDA_OK(cudaMalloc(&flat_mem, total));
+    flat_bytes = total;
+  }
+  ++generation;  // captured graphs assume the previous layout (and allocation) of the rasters
+  DYF_CUDA_OK(cudaMemsetAsync(flat_mem, 0, flat_bytes, s));
+  flat_offs = offs;
+  flat_G = G; flat_calls = cap;
+  return 0;
+}
 
 size_t Net::workspace_bytes(int rows) const {
   size_t total = 0;
@@ -835,6 +918,63 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.heads = 4;
         p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = o.type == OP_LINATTN ? launch_linear_attention(p, s) : launch_attention(p, s);
+        break;
+      }
+      case OP_FLAT_PACK: {
+        const int G = group_rows, calls = rows / group_rows;
+        rc = ensure_flat(G, calls, s);
+        if (rc) break;
+        const ConvLayer& c0 = convs[ops[1].layer];
+        const FlatGeo g = flat_geo(d.height, d.width, flats[0].k, G);
+        FlatPackParams p{};
+        const long long plane = (long long)d.height * d.width;
+        for (int i = 0; i < nsrc; ++i)
+          for (int cc = 0; cc < src_ch[i]; ++cc, ++p.n_slots) {
+            if (p.n_slots >= 16) { set_error("internal: flat pack supports <= 16 input channels"); return DYF_ERR_STATE; }
+            p.slot_ptr[p.n_slots] = srcs[i] + (size_t)cc * plane;
+            p.slot_rstride[p.n_slots] = (long long)src_ch[i] * plane;
+          }
+        p.src_rows = src_rows > 0 ? src_rows : rows; p.rows = rows; p.H = d.height; p.W = d.width;
+        p.k = flats[0].k; p.G = G; p.CP = c0.flat_cp; p.Cflat = flats[0].C; p.S = g.S; p.PI = g.PI; p.PC = g.PC;
+        p.out = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[0]);
+        if (noise_src >= 0) { set_error("data+noise conditioning is not built for the flat-raster path"); return DYF_ERR_UNSUPPORTED; }
+        rc = launch_pack_flat(p, s);
+        break;
+      }
+      case OP_FLAT_CONV: {
+        const ConvLayer& c = convs[o.layer];
+        const int G = group_rows, calls = rows / group_rows, k = c.KH, pad = (k - 1) / 2;
+        const FlatGeo gi = flat_geo(d.height, d.width, k, G);
+        FlatConvParams p{};
+        p.in = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.in0]);
+        p.w = wq_umma + c.flat_off; p.wrep = flat_weight_replicas(); p.wrep_stride = c.flat_elems;
+        p.H = d.height; p.W = d.width; p.G = G; p.calls = calls;
+        p.S_in = gi.S; p.PI_in = gi.PI; p.PC_in = gi.PC;
+        if (o.aux) {  // last layer: plain NHWC [rows][H][W][64]
+          p.out = bp[o.out]; p.S_out = d.width; p.PI_out = d.height * d.width; p.PC_out = G * p.PI_out;
+          if (o.aux == 2) {  // ... or straight to the network output through the fused 1x1 head
+            const ConvLayer& hc = convs[o.c0];
+            p.head_w = packed + params[hc.w].off; p.head_b = packed + params[hc.b].off; p.head_out = y; p.head_oc = d.out_channels;
+          }
+        } else {
+          const FlatGeo go = flat_geo(d.height, d.width, flats[o.out].k, G);
+          p.out = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.out]);
+          p.S_out = go.S; p.PI_out = go.PI; p.PC_out = go.PC;
+        }
+        p.res = o.res >= 0 ? p.in : nullptr;
+        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
+        p.Cin = c.flat_cin;
+        if (c.flat_first) {  // horizontal taps live in the channel axis: k vertical taps
+          p.ntaps = k; p.halo = pad * gi.S;
+          for (int ky = 0; ky < k; ++ky) p.shift[ky] = (ky - pad) * gi.S;
+        } else {
+          p.ntaps = k * k; p.halo = pad * gi.S + pad;
+          for (int t = 0; t < k * k; ++t) p.shift[t] = (t / k - pad) * gi.S + (t % k - pad);
+        }
+        p.act = o.act; p.flops_k = (double)c.Cin * k * k;
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
+        rc = launch_conv_flat(p, s);
         break;
       }
       default: set_error("internal: unknown op"); return DYF_ERR_STATE;

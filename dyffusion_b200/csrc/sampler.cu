@@ -59,9 +59,13 @@ int Sampler::plan() {
   return 0;
 }
 
-static int batch_cap(const dyf_sampler_desc& d, int rows) {
-  // logical interpolator calls per launch sequence; a cold-sampling step needs two (t = s_next and t = s)
-  int cap = d.max_rows_per_call > 0 ? std::max(d.max_rows_per_call, 2 * rows) : std::max(2 * rows, 256);
+static int batch_cap(const dyf_sampler_desc& d, int rows, int cells) {
+  // logical interpolator calls per launch sequence; a cold-sampling step needs two (t = s_next and t = s).  Default cap on
+  // the rows of one launch sequence: 256, or -- for small grids, whose network calls are launch-latency-bound -- what keeps
+  // about 2 M grid cells in flight (spring-mesh 10 x 10: 4096 rows, i.e. the refinement calls of a 200-row job run 20 at
+  // a time instead of 2)
+  const int by_cells = std::min(4096, (2 << 20) / std::max(1, cells));
+  int cap = d.max_rows_per_call > 0 ? std::max(d.max_rows_per_call, 2 * rows) : std::max(2 * rows, std::max(256, by_cells));
   return std::max(2, cap / rows);
 }
 
@@ -84,7 +88,7 @@ static size_t stage_bytes(const Sampler& sm, int rows, size_t* off_ic, size_t* o
 size_t Sampler::workspace_bytes(int rows) const {
   const size_t plane = (size_t)F->d.height * F->d.width;
   const size_t state = align256((size_t)rows * d.channels * plane * sizeof(float));
-  const int k = batch_cap(d, rows);
+  const int k = batch_cap(d, rows, F->d.height * F->d.width);
   size_t total = 2 * state;                                                    // x_s, x0_hat
   total += align256((size_t)k * rows * d.channels * plane * sizeof(float));     // interpolator outputs
   total += std::max(F->workspace_bytes(rows), I->workspace_bytes(k * rows));
@@ -106,7 +110,7 @@ int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds,
   const int N = d.num_timesteps, n = (int)schedule.size(), C = d.channels;
   const size_t plane = (size_t)F->d.height * F->d.width;
   const size_t state_n = (size_t)rows * C * plane;
-  const int kmax = batch_cap(d, rows);
+  const int kmax = batch_cap(d, rows, F->d.height * F->d.width);
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* x_s = reinterpret_cast<float*>(base); base += align256(state_n * sizeof(float));
@@ -148,7 +152,7 @@ int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds,
     return F->forward(rows, srcs, ch, ns, nullptr, x0_hat, r, net_ws, net_ws_bytes, s, noise_src, noise_w, rows, rows, &th);
   };
   // k logical interpolator calls at times t[0..k) sharing the inputs (ic, x0_hat); outputs land in ybuf[j]
-  auto run_I = [&](const double* t, int k) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
+  auto run_I = [&](const double* t, int k, float* out = nullptr) -> int {  // q_sample (:140-163) + _interpolate (:480-494)
     const float* srcs[4];
     int ch[4];
     int ns = 0;
@@ -161,7 +165,7 @@ int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds,
     r.on = d.enable_interpolator_dropout != 0 || d.forecaster_dropout != 0;
     r.stream = call;  // logical call j of the batch draws from stream call + j
     call += k;
-    return I->forward(k * rows, srcs, ch, ns, nullptr, ybuf, r, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows, th.data());
+    return I->forward(k * rows, srcs, ch, ns, nullptr, out ? out : ybuf, r, net_ws, net_ws_bytes, s, -1, 0.f, rows, rows, th.data());
   };
 
   for (int i = 0; i < n; ++i) {
@@ -206,9 +210,12 @@ int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds,
   // refinement of the intermediate predictions with the final x0_hat (:408-422)
   for (size_t j0 = 0; j0 < refine.size(); j0 += kmax) {
     const int k = (int)std::min<size_t>(kmax, refine.size() - j0);
-    int rc = run_I(&refine[j0], k);
+    bool consecutive = true;  // output slots of this batch back to back: the interpolator writes them in place
+    for (int j = 1; j < k; ++j) consecutive = consecutive && refine_slot[j0 + j] == refine_slot[j0] + j;
+    float* const dst = consecutive ? preds + (size_t)refine_slot[j0] * state_n : ybuf;
+    int rc = run_I(&refine[j0], k, dst);
     if (rc) return rc;
-    for (int j = 0; j < k; ++j)
+    for (int j = 0; j < k && !consecutive; ++j)
       DYF_CUDA_OK(cudaMemcpyAsync(preds + (size_t)refine_slot[j0 + j] * state_n, ybuf + (size_t)j * state_n,
                                   state_n * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }

@@ -110,7 +110,7 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_act_dtype", "dyf_nvtx_enab
             "dyf_boundary_conditions_spring_mesh", "dyf_window_gather", "dyf_adamw_workspace_bytes",
             "dyf_grad_sq_norm", "dyf_adamw_step"]
 KERNEL_CLASSES = ["conv_mma", "conv_umma", "pack", "upsample", "groupnorm", "readout", "time_tables", "elementwise",
-                  "attention", "conv_up"]
+                  "attention", "conv_up", "conv_flat"]
 
 
 class EngineError(RuntimeError):

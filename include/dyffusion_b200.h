@@ -97,7 +97,7 @@ uint64_t dyf_launch_count(void);
  * device time [ms], algorithmic FLOPs, algorithmic bytes and launch count since the last read; arrays must hold
  * DYF_KC_COUNT entries. */
 enum { DYF_KC_CONV_MMA = 0, DYF_KC_CONV_UMMA, DYF_KC_PACK, DYF_KC_UPSAMPLE, DYF_KC_GROUPNORM, DYF_KC_READOUT,
-       DYF_KC_TIME, DYF_KC_ELEMENTWISE, DYF_KC_ATTENTION, DYF_KC_CONV_UP, DYF_KC_COUNT };
+       DYF_KC_TIME, DYF_KC_ELEMENTWISE, DYF_KC_ATTENTION, DYF_KC_CONV_UP, DYF_KC_CONV_FLAT, DYF_KC_COUNT };
 int dyf_profile_enable(int32_t on);
 /* Restrict the event bracketing to one kernel class (DYF_KC_*; -1 = all classes): lets bench.py time its dominant kernel
  * live inside the timed region without putting event records between every other pair of launches. */
