@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdyffusion_b200.so")
-SOURCES = ["abi.cu", "net.cu", "sampler.cu", "conv_mma.cu", "conv_umma.cu", "conv_up.cu", "conv_flat.cu", "aux_kernels.cu", "attn_kernels.cu", "metrics_kernels.cu",
+SOURCES = ["abi.cu", "net.cu", "sampler.cu", "conv_mma.cu", "conv_umma.cu", "conv_up.cu", "conv_flat.cu", "aux_kernels.cu", "attn_kernels.cu", "attn_fused.cu", "metrics_kernels.cu",
            "dataset_kernels.cu", "optim_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden", "-Xptxas", "-v"]

@@ -346,7 +346,13 @@ int launch_linear_attention(const AttnParams& p, cudaStream_t s) {
   return 0;
 }
 
+int launch_attention_mma(const AttnParams& p, cudaStream_t s);  // attn_fused.cu
+
 int launch_attention(const AttnParams& p, cudaStream_t s) {
+  {  // tensor-core kernel for bottleneck grids (n <= 256); larger grids keep the shared-memory SIMT kernel below
+    const int rc = launch_attention_mma(p, s);
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
   if (p.n > 576) {
     set_error("full attention is built for bottleneck grids (n <= 576 positions = 24 x 24, K/V/P resident in shared memory); "
               "keep_spatial_dims on large grids needs the streaming-softmax variant");

@@ -115,6 +115,24 @@ struct AttnParams {
   DropCfg drop;              // dropout on the attention probabilities (full attention, attention.py:59,70)
 };
 int launch_linear_attention(const AttnParams& p, cudaStream_t s);
+// Fused linear-attention block (attn_fused.cu): y = x + to_out(LinearAttention(Dropout(LayerNorm(x)))) in two tensor-core
+// kernels; weights are the fp16 [Cout][K] rows of the generic conv weight pack (Net::wq).
+struct LinAttnFusedParams {
+  const act_t* x;        // [rows, n, C] block input (also the residual)
+  act_t* y;              // [rows, n, C]
+  const float* g;        // [C] LayerNorm gain
+  const act_t* w_qkv;    // to_qkv.1.weight [3 * 128][ldw]: q | k | v rows, heads-major
+  const act_t* w_out;    // to_out.weight [C][ldw_out]
+  const float* b_out;    // to_out.bias [C]
+  float* part;           // scratch: rows * linattn_fused_scratch_floats(n) floats
+  int rows, n, C, ldw, ldw_out;
+  int chunks, chunk_pix; // set by the launcher
+  act_t* ctx16;          // set by the launcher: combined context per row behind the partials
+  DropCfg drop;          // dropout on the LayerNorm output (attention.py:13)
+};
+int launch_linattn_fused(const LinAttnFusedParams& p, cudaStream_t s);
+bool linattn_fused_shape_ok(int C, int heads);
+size_t linattn_fused_scratch_floats(int n);
 int launch_attention(const AttnParams& p, cudaStream_t s);
 
 // ---- time embedding -> per-layer epilogue tables

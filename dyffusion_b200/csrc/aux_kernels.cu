@@ -1,5 +1,9 @@
 // Memory-bound kernels around the convolutions (see aux.cuh).  All activations are bf16 NHWC with 128-bit accesses
 // (8 channels per thread); network inputs/outputs are the reference's fp32 NCHW tensors.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "aux.cuh"
 
 namespace dyf {
@@ -389,6 +393,135 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormPar
   *reinterpret_cast<uint4*>(p.y + (size_t)m * p.C + c0) = pack8(f);
 }
 
+// One-kernel GroupNorm: a CLUSTER of CS CTAs per batch row, each walking its slice of the row twice -- first pass: per-thread
+// sums of a fixed 8-channel chunk, reduced in a fixed order inside the CTA, then across the cluster through distributed
+// shared memory (rank order: bit-reproducible); second pass: y = act(x * A + B) -> dropout -> + residual.  The slice
+// (<= 64 KB) was just streamed by the same CTA, so the second read hits L2: DRAM traffic is one read and one write of the
+// tensor instead of two reads and one write, and one launch replaces three.
+constexpr int GNF_THREADS = 256, GNF_UNROLL = 4;
+__global__ void __launch_bounds__(GNF_THREADS, 4) groupnorm_fused_kernel(const GroupNormParams p, int CS, int pix_per_cta) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float s_part[GNF_THREADS][2];
+  __shared__ float s_sum[64][2];   // this CTA's per-group partial sums (read by the other CTAs of the cluster)
+  __shared__ float s_grp[64][2];   // mean, rstd
+  extern __shared__ __align__(16) float s_ab[];  // [2][C]
+  const int r = blockIdx.x / CS, rank = blockIdx.x - r * CS;
+  const int chunks = p.C >> 3, cpg = p.C / p.G;
+  const int ch = threadIdx.x % chunks, lane_px = threadIdx.x / chunks, pstep = GNF_THREADS / chunks;
+  const int p_beg = rank * pix_per_cta, p_end = min(p.HW, p_beg + pix_per_cta);
+  const act_t* x = p.x + (size_t)r * p.HW * p.C + (ch << 3);
+  float s1 = 0.f, s2 = 0.f;
+  int px = p_beg + lane_px;
+  for (; px + (GNF_UNROLL - 1) * pstep < p_end; px += GNF_UNROLL * pstep) {
+    uint4 u[GNF_UNROLL];
+#pragma unroll
+    for (int k = 0; k < GNF_UNROLL; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(px + k * pstep) * p.C));
+#pragma unroll
+    for (int k = 0; k < GNF_UNROLL; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
+    }
+  }
+  for (; px < p_end; px += pstep) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)px * p.C)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
+  }
+  s_part[threadIdx.x][0] = s1;
+  s_part[threadIdx.x][1] = s2;
+  __syncthreads();
+  for (int half = pstep >> 1; half > 0; half >>= 1) {  // tree over the pixel lanes of every chunk (pstep is a power of two)
+    if ((int)threadIdx.x < half * chunks) {
+      s_part[threadIdx.x][0] += s_part[threadIdx.x + half * chunks][0];
+      s_part[threadIdx.x][1] += s_part[threadIdx.x + half * chunks][1];
+    }
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < p.G) {  // chunks of a group in index order
+    const int g = threadIdx.x, cpc = cpg >> 3;
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpc; c < (g + 1) * cpc; ++c) { a += s_part[c][0]; b += s_part[c][1]; }
+    s_sum[g][0] = a;
+    s_sum[g][1] = b;
+  }
+  cluster.sync();  // every CTA's partial sums are in place (also a CTA barrier)
+  if ((int)threadIdx.x < p.G) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < CS; ++k) {  // rank order
+      const float* remote = cluster.map_shared_rank(&s_sum[0][0], k);
+      a += remote[2 * g];
+      b += remote[2 * g + 1];
+    }
+    const float n = (float)p.HW * (float)cpg;
+    const float mean = a / n;
+    s_grp[g][0] = mean;
+    s_grp[g][1] = rsqrtf(fmaxf(b / n - mean * mean, 0.f) + p.eps);
+  }
+  cluster.sync();  // remote reads done before any CTA of the cluster may exit; s_grp visible
+  for (int c = threadIdx.x; c < p.C; c += GNF_THREADS) {  // A = rstd gamma (scale + 1), B = (beta - mean rstd gamma) (scale + 1) + shift
+    const int g = c / cpg;
+    float A = s_grp[g][1] * __ldg(p.gamma + c);
+    float B = __ldg(p.beta + c) - s_grp[g][0] * A;
+    if (p.tabA) {
+      const float tA = __ldg(p.tabA + (size_t)(r / p.tab_div) * p.C + c), tB = __ldg(p.tabB + (size_t)(r / p.tab_div) * p.C + c);
+      A *= tA;
+      B = B * tA + tB;
+    }
+    s_ab[c] = A;
+    s_ab[p.C + c] = B;
+  }
+  __syncthreads();
+  // (the per-channel A / B stay in shared memory: registers buy occupancy here -- the pass is latency- and issue-bound)
+  const float4* const sA4 = reinterpret_cast<const float4*>(s_ab + (ch << 3));
+  const float4* const sB4 = reinterpret_cast<const float4*>(s_ab + p.C + (ch << 3));
+  const DropRow dr = drop_row(p.drop, r, (uint64_t)p.HW * p.C);
+  act_t* y = p.y + (size_t)r * p.HW * p.C + (ch << 3);
+  const act_t* res = p.res ? p.res + (size_t)r * p.HW * p.res_ld + (ch << 3) : nullptr;
+  constexpr int AU = 2;  // pixels in flight per thread in the apply pass
+  for (px = p_beg + lane_px; px < p_end; px += AU * pstep) {
+    uint4 u[AU], rr[AU];
+#pragma unroll
+    for (int k = 0; k < AU; ++k) {
+      const int q = px + k * pstep;
+      if (q < p_end) {
+        u[k] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)q * p.C));
+        if (res) rr[k] = __ldg(reinterpret_cast<const uint4*>(res + (size_t)q * p.res_ld));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < AU; ++k) {
+      const int q = px + k * pstep;
+      if (q >= p_end) break;
+      float f[8];
+      unpack8(u[k], f);
+      {
+        const float4 a0 = sA4[0], a1 = sA4[1], b0 = sB4[0], b1 = sB4[1];
+        f[0] = apply_act(fmaf(f[0], a0.x, b0.x), p.act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), p.act);
+        f[2] = apply_act(fmaf(f[2], a0.z, b0.z), p.act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), p.act);
+        f[4] = apply_act(fmaf(f[4], a1.x, b1.x), p.act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), p.act);
+        f[6] = apply_act(fmaf(f[6], a1.z, b1.z), p.act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), p.act);
+      }
+      if (p.drop.thresh) {
+        const uint32_t keep = drop_keep_bits8(p.drop, dr, (uint64_t)q * p.C + (ch << 3));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop.scale : 0.f;
+      }
+      if (res) {
+        float g[8];
+        unpack8(rr[k], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += g[j];
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)q * p.C) = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ NS readout
 constexpr int RO_MAXC = 4;
 __global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
@@ -763,6 +896,26 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
   if (p.C % (8 * p.G) != 0 || chunks > 256 || 256 % chunks != 0 || p.G > 64) {
     set_error("groupnorm: unsupported channel/group configuration");
     return -1;
+  }
+  static const bool no_fuse = getenv("DYF_DISABLE_GN_FUSE") != nullptr;
+  if (!no_fuse && GNF_THREADS % chunks == 0 && chunks <= GNF_THREADS / 2 && (size_t)p.HW * p.C * sizeof(act_t) <= (1u << 20)) {
+    // rows of <= 1 MB: a cluster of up to 8 CTAs per row (~64 KB each), the second pass re-reads the slice from L2
+    const size_t row_bytes = (size_t)p.HW * p.C * sizeof(act_t);
+    int CS = 1;
+    while (CS < 8 && row_bytes / CS > (64u << 10)) CS *= 2;
+    const int pstep = GNF_THREADS / chunks;
+    const int per = cdiv(cdiv(p.HW, CS), pstep) * pstep;  // pixels per CTA (whole pixel-lane rounds)
+    ProfScope prof(s, KC_GROUPNORM);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(p.rows * CS)); cfg.blockDim = dim3(GNF_THREADS);
+    cfg.dynamicSmemBytes = 2 * p.C * sizeof(float); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DYF_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel, p, CS, per));
+    count_launch();
+    return 0;
   }
   const int pstep = 256 / chunks;
   int pix_per_block = pstep * 16;

@@ -49,7 +49,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN, OP_FLAT_PACK, OP_FLAT_CONV };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN, OP_FLAT_PACK, OP_FLAT_CONV, OP_LINATTN_FUSED };
 constexpr int BUF_NONE = -1;
 
 struct Op {

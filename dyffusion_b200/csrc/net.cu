@@ -446,6 +446,19 @@ int Net::attention_block(const std::string& Q, int x, int C, bool linear, int& s
   LNLayer ln; ln.C = C;
   ln.g = add_param(Q + ".fn.norm.g", {1, C, 1, 1});
   lns.push_back(ln);
+  if (linear && linattn_fused_shape_ok(C, heads) && !getenv("DYF_DISABLE_ATTN_FUSE")) {
+    // the whole block (LayerNorm, dropout, qkv, both attention contractions, output projection, residual) as two
+    // tensor-core kernels (attn_fused.cu); parameters are registered in the reference's module order as below
+    const int qi = add_conv(Q + ".fn.fn.to_qkv.1", C, 3 * hidden, 1, 1, 0, /*bias=*/false);
+    const int oi = add_conv(Q + ".fn.fn.to_out", hidden, C, 1, 1, 0);
+    const int out = add_buf(H, W, C);
+    Op f{}; f.type = OP_LINATTN_FUSED; f.in0 = x; f.out = out; f.layer = (int)lns.size() - 1; f.c0 = qi; f.c1 = oi;
+    f.drop_p = d.attn_dropout; f.site = site++;
+    const size_t fl = linattn_fused_scratch_floats(H * W);
+    f.aux = add_buf(1, 1, (int)(fl * 2));  // fp32 partials per row (buffer sizes count 2-byte elements)
+    ops.push_back(f);
+    return out;
+  }
   int y = add_buf(H, W, C);
   Op l{}; l.type = OP_CHANNEL_LN; l.in0 = x; l.out = y; l.layer = (int)lns.size() - 1;
   if (linear) { l.drop_p = d.attn_dropout; l.site = site++; }  // Dropout on the qkv input (attention.py:13)
@@ -918,6 +931,20 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.heads = 4;
         p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = o.type == OP_LINATTN ? launch_linear_attention(p, s) : launch_attention(p, s);
+        break;
+      }
+      case OP_LINATTN_FUSED: {
+        const LNLayer& l = lns[o.layer];
+        const ConvLayer& cq = convs[o.c0];
+        const ConvLayer& co = convs[o.c1];
+        LinAttnFusedParams p{};
+        p.x = bp[o.in0]; p.y = bp[o.out]; p.g = packed + params[l.g].off;
+        p.w_qkv = wq + cq.wq_off; p.ldw = cq.Kpad;
+        p.w_out = wq + co.wq_off; p.ldw_out = co.Kpad; p.b_out = packed + params[co.b].off;
+        p.part = reinterpret_cast<float*>(bp[o.aux]);
+        p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.C = l.C;
+        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
+        rc = launch_linattn_fused(p, s);
         break;
       }
       case OP_FLAT_PACK: {
