@@ -22,7 +22,12 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bf16: bool = False) -> str:
+    """bf16=True (or DYF_ACT_BF16=1 in the environment) builds the bf16-storage variant as libdyffusion_b200_bf16.so
+    (load it with DYF_LIB=<path>; A/B measurements of the 16-bit storage type)."""
+    bf16 = bf16 or os.environ.get("DYF_ACT_BF16") == "1"
+    if bf16:
+        return _build_variant("bf16", ["-DDYF_ACT_BF16"], verbose)
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -49,6 +54,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(log))
     return LIB
+
+
+def _build_variant(tag: str, defines, verbose: bool) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    lib = os.path.join(HERE, f"libdyffusion_b200_{tag}.so")
+    bdir = os.path.join(HERE, "build", tag)
+    os.makedirs(bdir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *defines, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src} ({tag}):\n{out}")
+    r = subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed ({tag}):\n{r.stdout}")
+    return lib
 
 
 if __name__ == "__main__":
