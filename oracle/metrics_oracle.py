@@ -9,10 +9,13 @@
   un-pinned in the reference's setup.py:96): members sorted, then the integral of (F_ens - F_obs)^2 accumulated member by
   member with equal weights.
 
-PARITY UNPINNED for this module: neither xskillscore nor properscoring is installed in the build image and the reference
-ships no metric fixtures, so the restatement could not be run against the libraries themselves.  It is pinned instead
-(tests/test_metrics_cpu.py) against the closed form the algorithm integrates, CRPS = E|X - y| - 1/2 E|X - X'|, evaluated
-by brute force in float64, and against hand-computed small cases.
+Pinning: MSE, per-member MSE, spread-skill ratio and all shape / `mean_over_samples` bookkeeping are pinned against the
+reference's OWN `src/utilities/evaluation.py`, imported unmodified with stub `xarray` / `xskillscore` modules
+(tests/test_metrics_cpu.py::test_oracle_equals_the_reference_evaluation_module).  The CRPS kernel itself lives in third-party
+code that is absent here (xskillscore, un-pinned in the reference's setup.py:96 -> properscoring 0.1
+`_crps_ensemble_vectorized`): for that one function parity stays "unpinned against the library"; it is pinned to the published
+algorithm restated below, to the closed form it integrates, CRPS = E|X - y| - 1/2 E|X - X'| (brute force, float64), and to
+hand-computed cases.
 """
 from __future__ import annotations
 
