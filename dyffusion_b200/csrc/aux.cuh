@@ -18,6 +18,8 @@ struct PackParams {
   int ones_channel;        // output channel set to 1.0 inside the image (carries a folded bias), -1 = none
   int s2d;                 // 1: space-to-depth packing -- output pixel (by, bx) holds the 2x2 block of the (resized)
                            //    grid as 4 sub-positions x 16 channel slots (slot `ones_channel` of each = 1.0)
+                           // 2: x-im2col for a 7x7 stem -- 64 output channels = 7 horizontal taps x 8 channel slots
+  int noise_c0, noise_c1;  // set by the launcher (x-im2col): flattened channel range of the noisy source
   int noise_src;           // -1 = none
   float noise_w;
   uint64_t seed, stream;
@@ -25,6 +27,16 @@ struct PackParams {
   uint32_t rng_rows, row_off;  // rows per logical call / global index of the first row (see DropCfg)
 };
 int launch_pack(const PackParams& p, cudaStream_t s);
+int launch_stem_xim2col_weight(const float* w, float* out, int O, int C, cudaStream_t s);  // [O][C][7][7] -> [O][64][7]
+struct Head1x1Params {
+  const act_t* x;      // [M][C]
+  const float* w;      // [OC][C] fp32
+  const float* bias;   // [OC] or nullptr
+  float* y;            // fp32 NCHW [rows][OC][HW]
+  long long M;
+  int C, OC, HW;
+};
+int launch_head1x1(const Head1x1Params& p, cudaStream_t s);
 
 // ---- fused stem of unet_simple: [bilinear resize ->] 1x1 conv (C_in <= 16 -> 64) + bias [+ input dropout],
 //      fp32 NCHW sources -> bf16 NHWC, never materialising the resized input (reference unet_simple.py:193 + :113-116)

@@ -118,6 +118,83 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const
   o[1] = pack8(v + 8);
 }
 
+// ------------------------------------------------------------------------------------------------ pack, x-im2col
+// fp32 NCHW sources -> 16-bit NHWC [rows, H, W, 64] whose channel kx * 8 + c holds source channel c of pixel (y, x + kx - 3)
+// (zero outside the image, c >= C_in, kx = 7): the horizontal taps of a 7x7 stem live in the channel axis, so the conv is
+// seven VERTICAL taps over 64 channels on the tcgen05 halo-patch kernel (conv_umma.cu, S1K7V).  "data+noise" conditioning is
+// applied per source element with the element-keyed Philox stream of pack_kernel (the seven copies of a pixel agree).
+__global__ void __launch_bounds__(256) pack_xim2col_kernel(const PackParams p, const S2dChannels ch) {
+  const long long total = (long long)p.rows * p.Ho * p.Wo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx % p.Wo);
+  const int y = (int)((idx / p.Wo) % p.Ho);
+  const int r = (int)(idx / ((long long)p.Wo * p.Ho));
+  const int rs = r % p.src_rows;
+  const size_t plane = (size_t)p.Hi * p.Wi;
+  uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)idx * 64);
+#pragma unroll
+  for (int kx = 0; kx < 7; ++kx) {
+    const int xs = x + kx - 3;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float val = 0.f;
+      if (c < ch.n && xs >= 0 && xs < p.Wi) {
+        val = __ldg(ch.plane[c] + (size_t)rs * ch.row_stride[c] + (size_t)y * p.Wi + xs);
+        if (c >= p.noise_c0 && c < p.noise_c1) {
+          const uint32_t jc = (uint32_t)r / p.rng_rows, rr = (uint32_t)r - jc * p.rng_rows + p.row_off;
+          const uint64_t e = ((uint64_t)rr * (p.noise_c1 - p.noise_c0) + (c - p.noise_c0)) * plane + (size_t)y * p.Wi + xs;
+          Philox ph(rng_seed(p.seed, p.seed_ptr));
+          uint4 rn = ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.stream + jc, 0x4e4f4953u);
+          val = p.noise_w * val + (1.f - p.noise_w) * gauss_from(rn.x, rn.y);
+        }
+      }
+      v[c] = val;
+    }
+    o[kx] = pack8(v);
+  }
+  o[7] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// 7x7 stem filter fp32 [O][C][7][7] -> [O][64][7]: (kx * 8 + c, ky), zero for the unused slots (the weight of the conv over
+// the x-im2col'd input)
+__global__ void stem_xim2col_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * 64 * 7) return;
+  const int ky = idx % 7, ci = (idx / 7) % 64, o = idx / (7 * 64);
+  const int kx = ci >> 3, c = ci & 7;
+  out[idx] = (kx < 7 && c < C) ? w[(((size_t)o * C + c) * 7 + ky) * 7 + kx] : 0.f;
+}
+
+// 1x1 head with a handful of output channels (SST final_conv 64 -> 1): y[row][oc][pixel] = w[oc] . x[row][pixel] + b[oc],
+// fp32 NCHW out.  One thread per pixel: a 128-bit load per 8 channels, weights broadcast from shared memory.
+__global__ void __launch_bounds__(256) head1x1_kernel(const Head1x1Params p) {
+  extern __shared__ float s_w[];  // [OC][C] + [OC]
+  for (int i = threadIdx.x; i < p.OC * p.C; i += blockDim.x) s_w[i] = p.w[i];
+  for (int i = threadIdx.x; i < p.OC; i += blockDim.x) s_w[p.OC * p.C + i] = p.bias ? p.bias[i] : 0.f;
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.M) return;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = o < p.OC ? s_w[p.OC * p.C + o] : 0.f;
+  const uint4* xp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.C);
+  for (int c8 = 0; c8 < p.C / 8; ++c8) {
+    float f[8];
+    unpack8(__ldg(xp + c8), f);
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < p.OC) {
+        const float* w = s_w + o * p.C + c8 * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], w[j], acc[o]);
+      }
+  }
+  const long long r = m / p.HW, pix = m - r * p.HW;
+  for (int o = 0; o < p.OC; ++o) p.y[((size_t)r * p.OC + o) * p.HW + pix] = acc[o];
+}
+
 // ------------------------------------------------------------------------------------------------ fused stem
 // One warp = 32 consecutive output pixels.  Phase 1: lane p gathers (bilinear) the C_in input values of pixel p --
 // neighbouring lanes read neighbouring source addresses of the same channel plane, so the gathers coalesce.
@@ -838,7 +915,40 @@ __global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
 
 }  // namespace
 
+int launch_head1x1(const Head1x1Params& p, cudaStream_t s) {
+  if (p.OC > 8 || p.C % 8) { set_error("head1x1: needs <= 8 output channels and C % 8 == 0"); return -1; }
+  ProfScope prof(s, KC_ELEMENTWISE, 2.0 * (double)p.M * p.C * p.OC, (double)p.M * (2.0 * p.C + 4.0 * p.OC));
+  head1x1_kernel<<<cdiv(p.M, 256), 256, (size_t)(p.OC * p.C + p.OC) * sizeof(float), s>>>(p);
+  DYF_LAUNCH_OK("head1x1_kernel");
+  return 0;
+}
+
+int launch_stem_xim2col_weight(const float* w, float* out, int O, int C, cudaStream_t s) {
+  stem_xim2col_weight_kernel<<<cdiv((long long)O * 64 * 7, 256), 256, 0, s>>>(w, out, O, C);
+  DYF_LAUNCH_OK("stem_xim2col_weight_kernel");
+  return 0;
+}
+
 int launch_pack(const PackParams& p, cudaStream_t s) {
+  if (p.s2d == 2) {  // x-im2col for a 7x7 stem (<= 8 input channels)
+    S2dChannels ch{};
+    PackParams q = p;
+    q.noise_c0 = q.noise_c1 = 0;
+    const size_t plane = (size_t)p.Hi * p.Wi;
+    for (int i = 0; i < p.nsrc; ++i) {
+      if (i == p.noise_src) { q.noise_c0 = ch.n; q.noise_c1 = ch.n + p.C[i]; }
+      for (int c = 0; c < p.C[i]; ++c, ++ch.n) {
+        if (ch.n >= 8) { set_error("pack x-im2col: needs <= 8 input channels"); return -1; }
+        ch.plane[ch.n] = p.src[i] + (size_t)c * plane;
+        ch.row_stride[ch.n] = (int)(p.C[i] * plane);
+      }
+    }
+    if (p.bilinear || p.Hi != p.Ho || p.Wi != p.Wo) { set_error("pack x-im2col: no resize"); return -1; }
+    ProfScope prof(s, KC_PACK);
+    pack_xim2col_kernel<<<cdiv((long long)p.rows * p.Ho * p.Wo, 256), 256, 0, s>>>(q, ch);
+    DYF_LAUNCH_OK("pack_xim2col_kernel");
+    return 0;
+  }
   if (p.s2d) {
     int ctot = 0;
     for (int i = 0; i < p.nsrc; ++i) ctot += p.C[i];

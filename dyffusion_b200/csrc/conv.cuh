@@ -162,5 +162,6 @@ bool conv_umma_shape_ok(int Cin_pad, int Cout, int k, int stride, int pad);
 int umma_padded_cout(int Cout);
 int launch_repack_umma(const float* w, act_t* out, int O, int I, int k, int stride, int pad, int standardize,
                        cudaStream_t s);
+int launch_repack_umma_k7v(const float* w, act_t* out, int O, cudaStream_t s);  // [O][64][7] -> 7-vertical-tap stage tiles
 
 }  // namespace dyf

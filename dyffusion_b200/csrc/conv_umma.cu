@@ -42,7 +42,9 @@ constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each drainin
 __host__ __device__ constexpr int prod_warps(bool tma) { return tma ? 1 : 8; }
 __host__ __device__ constexpr int cta_threads(bool tma) { return (EPI_WARPS + prod_warps(tma) + 2) * 32; }
 
-enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2, S2K2 = 3 };  // S2K2 (2x2 / stride 2 / pad 0) runs on the S1K1 kernel, see launch_s2k2
+enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2, S2K2 = 3, S1K7V = 4 };  // S2K2 (2x2 / stride 2 / pad 0) runs on the S1K1 kernel, see launch_s2k2
+// S1K7V: 7 VERTICAL taps (7x1 filter, pad 3 vertically, none horizontally) over 64 channels -- the SST stem (7x7, C_in <= 8)
+// after its horizontal taps were packed into the channel axis (pack_xim2col_kernel): TMA path only
 
 template <int MODE, int T = 1> struct Geo;  // T = pixel tiles side by side per work item (gathered patches: stride-2 mode only)
 template <int T> struct Geo<S1K3, T> {
@@ -71,6 +73,18 @@ template <int T> struct Geo<S1K1, T> {  // 1x1 convolution = plain GEMM over the
   __device__ static int slot(int pr, int pc) { return pr * PW + pc; }
   __device__ static int plane_of(int g, int) { return g; }
   __device__ static int in_y(int oy0, int pr) { return oy0 + pr; }
+  __device__ static int in_x(int ox0, int pc) { return ox0 + pc; }
+};
+template <int T> struct Geo<S1K7V, T> {  // (the gather-path members are placeholders: this mode only runs with TMA patches)
+  static constexpr int CH = 64, PLANES = 8, CPL = 8;
+  static constexpr int PH = TILE_H + 6, PW = TILE_W;
+  static constexpr int PIX = PH * PW, SLOTS = PIX;
+  static constexpr int TAPS = 7, KW = 1, GT = 1, HALO = 0;
+  static constexpr int SBO = PW * 16;
+  __device__ static int tap_offset(int ky, int, int) { return ky * PW * 16; }
+  __device__ static int slot(int pr, int pc) { return pr * PW + pc; }
+  __device__ static int plane_of(int g, int) { return g; }
+  __device__ static int in_y(int oy0, int pr) { return oy0 - 3 + pr; }
   __device__ static int in_x(int ox0, int pc) { return ox0 + pc; }
 };
 template <int T> struct Geo<S2K4, T> {
@@ -531,6 +545,8 @@ template <> struct Stages<S1K3, 64, true, 1> { static constexpr int T = 2, GT = 
 template <> struct Stages<S1K3, 128, true, 1> { static constexpr int T = 1, GT = 1, A = 3, B = 9; };  //  69 KB patches + 144 KB resident filter
 template <> struct Stages<S1K3, 64, false> { static constexpr int T = 1, GT = 3, A = 6, B = 3; };
 template <> struct Stages<S1K3, 128, false> { static constexpr int T = 1, GT = 3, A = 3, B = 3; };
+template <> struct Stages<S1K7V, 64, true> { static constexpr int T = 2, GT = 1, A = 3, B = 7; };    // 135 KB patches + 56 KB resident filter
+template <> struct Stages<S1K7V, 128, true> { static constexpr int T = 2, GT = 1, A = 2, B = 7; };   //  90 KB patches + 112 KB resident filter
 template <> struct Stages<S1K1, 64, true> { static constexpr int T = 2, GT = 1, A = 5, B = 4; };
 template <> struct Stages<S1K1, 128, true> { static constexpr int T = 2, GT = 1, A = 4, B = 4; };
 template <> struct Stages<S1K1, 64, true, 1> { static constexpr int T = 1, GT = 1, A = 6, B = 6; };   // grids <= 8 pixels wide
@@ -605,7 +621,9 @@ int s2k4_weights_chunk() {
   return (env_a && env_a[0] == 'c') ? 32 : 64;
 }
 
-int mode_of(int k, int stride, int pad) {
+int mode_of(int k, int stride, int pad, int kw = -1) {
+  if (k == 7 && kw == 1 && stride == 1 && pad == 3) return S1K7V;
+  if (kw >= 0 && kw != k) return -1;
   if (k == 3 && stride == 1 && pad == 1) return S1K3;
   if (k == 4 && stride == 2 && pad == 1) return S2K4;
   if (k == 1 && stride == 1 && pad == 0) return S1K1;
@@ -632,6 +650,9 @@ bool conv_umma_eligible(const ConvParams& p) {
     const int mode = mode_of(p.KH, p.stride, p.pad);
     if ((mode != S1K3 && mode != S1K1) || p.Cin0 <= 0 || p.Cin0 % 64 || (p.Cin - p.Cin0) % 64) return false;
   }
+  if (mode_of(p.KH, p.stride, p.pad, p.KW) == S1K7V)
+    return p.w_umma != nullptr && !p.in2 && p.Cin == 64 && (p.Cout == 64 || p.Cout % 128 == 0) && p.out_fp32 == 0 &&
+           ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
   return p.w_umma != nullptr && p.KH == p.KW && conv_umma_shape_ok(p.Cin, p.Cout, p.KH, p.stride, p.pad) &&
          p.out_fp32 == 0 && ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
 }
@@ -673,9 +694,10 @@ static int launch_s2k2(const ConvParams& p, cudaStream_t stream) {
 
 int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
   if (!conv_umma_eligible(p)) return 0;
-  if (mode_of(p.KH, p.stride, p.pad) == S2K2) return launch_s2k2(p, stream);
+  if (mode_of(p.KH, p.stride, p.pad, p.KW) == S2K2) return launch_s2k2(p, stream);
   const bool n64 = umma_tile_n(p.Cout) == 64;
-  const int mode = mode_of(p.KH, p.stride, p.pad);
+  const int mode = mode_of(p.KH, p.stride, p.pad, p.KW);
+  if (mode == S1K7V) return n64 ? launch_t<64, S1K7V, true>(p, stream) : launch_t<128, S1K7V, true>(p, stream);
   static const char* env_a = getenv("DYF_UMMA_A");  // "cpasync" forces the cp.async patch gather
   const bool want_tma = !(env_a && env_a[0] == 'c');
   // (descriptor base_offset stays 0: the 128-B swizzle is a function of absolute smem address bits for TMA writes
@@ -726,6 +748,14 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     return n64 ? launch_t<64, S2K4, true>(p, stream, it->second.m) : launch_t<128, S2K4, true>(p, stream, it->second.m);
   }
   return n64 ? launch_t<64, S2K4, false>(p, stream) : launch_t<128, S2K4, false>(p, stream);
+}
+
+// weights [O][64][7] (x-im2col'd stem filter, see launch_stem_xim2col_weight) -> S1K7V stage tiles
+int launch_repack_umma_k7v(const float* w, act_t* out, int O, cudaStream_t s) {
+  const long long total = (long long)umma_padded_cout(O) * 64 * 7;
+  repack_umma_kernel<<<cdiv(total, 256), 256, 0, s>>>(w, out, O, 64, umma_tile_n(O), 7, 64, 0);
+  DYF_LAUNCH_OK("repack_umma_kernel");
+  return 0;
 }
 
 int launch_repack_umma(const float* w, act_t* out, int O, int I, int k, int stride, int pad, int standardize,

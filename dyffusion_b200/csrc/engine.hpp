@@ -36,6 +36,7 @@ struct ConvLayer {
   long long wu_off = -1;                      // offset into Net::wq_umma (tcgen05 stage tiles) or -1
   long long up_off[DYF_UP_VARIANTS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // fused upsample+conv: composite variants in wq_umma
   long long flat_off = -1, flat_elems = 0;    // flat-raster path (conv_flat.cu): stage tiles in wq_umma (x replicas)
+  int stem_xim2col = 0;                       // 7x7 stem run as 7 vertical taps over the x-im2col'd input (64 channels)
   int flat_first = 0;                         // first layer: horizontal taps folded into the channel axis (CP slots per tap)
   int flat_cp = 0, flat_cin = 0;              // channel slots per horizontal tap, raster channels read by the layer
   long long na_off = -1, nb_off = -1;         // folded affine in Net::packed
@@ -49,7 +50,7 @@ struct NormLayer {  // GroupNorm applied by its own kernel
   long long stats_off = 0;  // floats per row offset in stats scratch
 };
 
-enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN, OP_FLAT_PACK, OP_FLAT_CONV, OP_LINATTN_FUSED };
+enum OpType { OP_STEM, OP_PACK, OP_CONV, OP_CONV_UP, OP_UPSAMPLE, OP_GROUPNORM, OP_READOUT, OP_READOUT_GATHER, OP_LINATTN, OP_ATTN, OP_CHANNEL_LN, OP_FLAT_PACK, OP_FLAT_CONV, OP_LINATTN_FUSED, OP_HEAD1X1 };
 constexpr int BUF_NONE = -1;
 
 struct Op {

@@ -485,10 +485,22 @@ int Net::build_unet_resnet() {
   if (d.groups != 8) { set_error("Unet: resnet_block_groups must be 8"); return DYF_ERR_UNSUPPORTED; }
   Hin = d.height; Win = d.width;
   int site = 1;
-  int xin = add_buf(Hin, Win, round_up(cin, 8));
-  Op pk{}; pk.type = OP_PACK; pk.out = xin; pk.bilinear = 0;
+  // 7x7 stem on the tcgen05 halo-patch kernel: horizontal taps packed into the channel axis (7 x 8 slots = 64 channels),
+  // seven vertical taps left (conv_umma.cu S1K7V); otherwise the generic mma.sync pipeline
+  const bool stem_umma = d.init_kernel == 7 && d.init_stride == 1 && d.init_padding == 3 && cin <= 8 &&
+                         (dim == 64 || dim % 128 == 0) && !getenv("DYF_DISABLE_STEM_UMMA") && !getenv("DYF_DISABLE_UMMA");
+  int xin = add_buf(Hin, Win, stem_umma ? 64 : round_up(cin, 8));
+  Op pk{}; pk.type = OP_PACK; pk.out = xin; pk.bilinear = 0; pk.aux = stem_umma ? 2 : 0;
   ops.push_back(pk);
   int ci = add_conv("init_conv", cin, dim, d.init_kernel, d.init_stride, d.init_padding);
+  if (stem_umma) {
+    ConvLayer& c = convs[ci];
+    c.stem_xim2col = 1;
+    c.flops_cin = cin * 7;                  // FLOP accounting: 7 taps x (7 cin) = the reference's 49 cin per pixel
+    c.Cpad = 64; c.KH = 7; c.KW = 1; c.K = 7 * 64; c.Kpad = 7 * 64;
+    c.wq_off = wq_elems; wq_elems += (size_t)dim * c.Kpad;
+    c.wu_off = (long long)wu_elems; wu_elems += (size_t)umma_padded_cout(dim) * 64 * 7;
+  }
   const int H0 = (Hin + 2 * d.init_padding - d.init_kernel) / d.init_stride + 1;
   const int W0 = (Win + 2 * d.init_padding - d.init_kernel) / d.init_stride + 1;
   int x = add_buf(H0, W0, dim);
@@ -566,8 +578,13 @@ int Net::build_unet_resnet() {
     x = resnet_block("final_res_block", cat, 2 * dim, dim, site);
   }
   int fl = add_conv("final_conv", dim, d.out_channels, 1, 1, 0);
-  Op f{}; f.type = OP_CONV; f.in0 = x; f.layer = fl; f.out_mode = 2;
-  ops.push_back(f);
+  if (d.out_channels <= 8 && !getenv("DYF_DISABLE_HEAD1X1")) {  // a few output channels: one dot product per pixel, fp32 weights
+    Op f{}; f.type = OP_HEAD1X1; f.in0 = x; f.layer = fl;
+    ops.push_back(f);
+  } else {
+    Op f{}; f.type = OP_CONV; f.in0 = x; f.layer = fl; f.out_mode = 2;
+    ops.push_back(f);
+  }
   if (bufs[x].H != d.height || bufs[x].W != d.width) { set_error("Unet: init_stride != 1 is not built"); return DYF_ERR_UNSUPPORTED; }
   return 0;
 }
@@ -629,6 +646,19 @@ int Net::finalize(cudaStream_t s) {
     }
     const float* w_src = packed + params[c.w].off;
     float* composed = nullptr;
+    if (c.stem_xim2col) {  // [O][cin][7][7] -> [O][64][7]: filter of the conv over the x-im2col'd input
+      float* ws = nullptr;
+      DYF_CUDA_OK(cudaMalloc(&ws, (size_t)c.Cout * 64 * 7 * sizeof(float)));
+      int rs = launch_stem_xim2col_weight(w_src, ws, c.Cout, c.Cin, s);
+      if (!rs) rs = launch_repack_umma_k7v(ws, wq_umma + c.wu_off, c.Cout, s);
+      if (!rs) rs = launch_repack_conv(ws, wq + c.wq_off, c.Cout, 64, 7, 1, 64, c.Kpad, 0, s);
+      const float* bias = c.b >= 0 ? packed + params[c.b].off : nullptr;
+      if (!rs) rs = launch_fold_norm(bias, nullptr, nullptr, nullptr, nullptr, 1e-5f, packed + c.na_off, packed + c.nb_off, c.Cout, s);
+      if (rs) return rs;
+      DYF_CUDA_OK(cudaStreamSynchronize(s));
+      DYF_CUDA_OK(cudaFree(ws));
+      continue;
+    }
     if (c.comp_s2d) {  // composite weights in plain conv layout [Cout, 64, 3, 3] (fp32 staging, freed below)
       DYF_CUDA_OK(cudaMalloc(&composed, (size_t)c.Cout * 576 * sizeof(float)));
       int rcc = launch_compose_s2d(packed + params[c.w].off, packed + params[c.comp_wi].off, packed + params[c.comp_bi].off,
@@ -825,6 +855,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.noise_src = noise_src; p.noise_w = noise_w; p.seed = rng.seed; p.stream = rng.stream; p.seed_ptr = rng.seed_ptr;
         p.rng_rows = rng.group_rows; p.row_off = rng.row_off; p.ones_channel = o.ones_channel;
         p.s2d = o.aux;
+        if (o.aux == 2) p.Cpad = 64;
         if (noise_src >= 0 && o.bilinear) { set_error("data+noise conditioning with an outer resize is unsupported"); return DYF_ERR_UNSUPPORTED; }
         rc = launch_pack(p, s);
         break;
@@ -838,6 +869,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.rows = rows; p.Hi = bi.H; p.Wi = bi.W; p.Cin = bi.C; p.Cin_real = c.flops_cin ? c.flops_cin : c.Cin;
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
+        if (c.stem_xim2col) p.Wo = bi.W;  // vertical taps only: no horizontal padding
         p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;
         p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
@@ -853,6 +885,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         }
         if (p.Cin != c.Cpad) { set_error("internal: conv input channel mismatch"); return DYF_ERR_STATE; }
         rc = launch_conv_umma(p, s);
+        if (rc == 0 && c.stem_xim2col) { set_error("internal: the x-im2col stem needs the tcgen05 TMA path"); return DYF_ERR_STATE; }
         if (rc == 0 && p.in2) { set_error("internal: two-source conv needs the tcgen05 TMA path"); return DYF_ERR_STATE; }
         if (rc == 0) rc = launch_conv_mma(p, s);
         else if (rc > 0) rc = 0;
@@ -931,6 +964,14 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.rows = rows; p.n = bufs[o.in0].H * bufs[o.in0].W; p.heads = 4;
         p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
         rc = o.type == OP_LINATTN ? launch_linear_attention(p, s) : launch_attention(p, s);
+        break;
+      }
+      case OP_HEAD1X1: {
+        const ConvLayer& c = convs[o.layer];
+        Head1x1Params p{};
+        p.x = bp[o.in0]; p.w = packed + params[c.w].off; p.bias = c.b >= 0 ? packed + params[c.b].off : nullptr; p.y = y;
+        p.HW = bufs[o.in0].H * bufs[o.in0].W; p.M = (long long)rows * p.HW; p.C = bufs[o.in0].C; p.OC = c.Cout;
+        rc = launch_head1x1(p, s);
         break;
       }
       case OP_LINATTN_FUSED: {
