@@ -113,7 +113,7 @@ int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
 
 // ---- spring-mesh layers on flat padded rasters (conv_flat.cu)
 struct FlatGeo { int p, S, PI, PC; };  // halo width, row stride, positions per image, positions per logical call
-FlatGeo flat_geo(int H, int W, int k, int G);      // raster read by a k x k layer, G rows per logical call
+FlatGeo flat_geo(int H, int W, int k, int G, bool hgap = true);  // raster read by a k x k layer, G rows per logical call
 bool conv_flat_shape_ok(int H, int W, int k, int Cout);
 struct FlatConvParams {
   const act_t* in;        // raster of this layer [calls * PC_in][Cin]
@@ -149,6 +149,9 @@ struct FlatPackParams {
 };
 int launch_pack_flat(const FlatPackParams& p, cudaStream_t s);
 int launch_conv_flat(const FlatConvParams& p, cudaStream_t stream);
+#define FLAT_MAX_LAYERS 4
+// up to FLAT_MAX_LAYERS consecutive layers of one network call in ONE persistent kernel (grid-wide barriers in between)
+int launch_conv_flat_net(const FlatConvParams* layers, int nlayers, cudaStream_t stream);
 int flat_weight_replicas();  // copies of every flat layer's filter kept in global memory (DYF_FLAT_WREP, default 8)
 int launch_repack_flat(const float* w, act_t* out, int Cin, int k, cudaStream_t s);
 int launch_repack_flat_first(const float* w, act_t* out, int Cin, int k, int CP, int Cflat, cudaStream_t s);

@@ -20,6 +20,8 @@
 //
 // Pipeline = conv_umma.cu's: persistent warp-specialised CTAs (8 epilogue warps, TMA patch producer, MMA issuer, weight
 // producer), weights as 8 KB stage tiles by bulk TMA, two ping-pong TMEM accumulator sets.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -44,16 +46,28 @@ struct __align__(8) FBarriers {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) conv_flat_kernel(const FlatConvParams p, const __grid_constant__ CUtensorMap tmap,
-                                                               int a_stage, int box_rows, int nbox, int num_work, int items_per_call,
-                                                               int BS) {
+// Launch-side geometry of one layer, and the whole network call: up to FLAT_MAX_LAYERS layers run inside ONE persistent
+// kernel (cooperative launch), separated by grid-wide barriers -- a layer reads, through TMA, raster positions that other
+// CTAs' epilogues wrote.  All pipelines (patch ring, weight ring, TMEM ping-pong) keep their state across the layers.
+struct FlatLayerCfg { int box_rows, nbox, num_work, items_per_call; };
+struct FlatNetParams {
+  int nlayers, BS, a_stage;   // weight-ring depth, patch stage stride (the largest layer's)
+  FlatConvParams L[FLAT_MAX_LAYERS];
+  FlatLayerCfg G[FLAT_MAX_LAYERS];
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_constant__ FlatNetParams P,
+                                                                   const __grid_constant__ CUtensorMap tm0,
+                                                                   const __grid_constant__ CUtensorMap tm1,
+                                                                   const __grid_constant__ CUtensorMap tm2,
+                                                                   const __grid_constant__ CUtensorMap tm3) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int a_stage = P.a_stage, BS = P.BS;
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS * a_stage;
   FBarriers* bars = reinterpret_cast<FBarriers*>(sB + BS * B_STAGE);
   float* sTab = reinterpret_cast<float*>(sB + BS * B_STAGE + ((sizeof(FBarriers) + 15) & ~15));  // [2][A | B][64]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunks = p.Cin / 64;
   constexpr int MMA_WARP = EPI_WARPS + 1;
 
   if (tid == 0) {
@@ -71,6 +85,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_kernel(const FlatConvPar
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // pipeline state of this thread's role, carried across the layers
+  int e_it = 0;                                        // epilogue: items drained so far
+  int a_ca = 0;                                        // patch producer: stages issued so far
+  int m_sa = 0, m_pa = 0, m_sb = 0, m_pb = 0, m_it = 0;  // MMA issuer: ring positions / parities, items issued
+  int w_sb = 0, w_pb = 1;                              // weight producer
+
+  for (int layer = 0; layer < P.nlayers; ++layer) {
+  const FlatConvParams& p = P.L[layer];
+  const int box_rows = P.G[layer].box_rows, nbox = P.G[layer].nbox, num_work = P.G[layer].num_work,
+            items_per_call = P.G[layer].items_per_call;
+  const int nchunks = p.Cin / 64;
   if (warp < EPI_WARPS) {
     // =============================== epilogue: TMEM -> tables / activation / dropout / residual -> next raster ==========
     // Plain layers: warp = (TMEM lane quarter, column half), both tiles.  Last layer with the 1x1 head fused in
@@ -87,8 +112,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_kernel(const FlatConvPar
       if (tid < 8) sHead[BN * 8 + tid] = tid < p.head_oc ? __ldg(p.head_b + tid) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     }
-    int it = 0, tab_key = -1, tab_buf = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    int tab_key = -1, tab_buf = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++e_it) {
+      const int it = e_it;
       const int call = w / items_per_call, t0 = (w - call * items_per_call) * ITEM_POS;
       const int acc = it & 1;
       if (call != tab_key) {  // epilogue tables of this logical call -> shared memory (other buffer: one barrier suffices)
@@ -194,18 +220,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_kernel(const FlatConvPar
   } else if (warp == EPI_WARPS) {
     // =============================== patch producer: nbox TMA boxes of consecutive positions per channel chunk ==========
     if (lane == 0) {
-      int ca = 0;
+      const CUtensorMap* tm = layer == 0 ? &tm0 : layer == 1 ? &tm1 : layer == 2 ? &tm2 : &tm3;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int call = w / items_per_call, t0 = (w - call * items_per_call) * ITEM_POS;
         const int g0 = call * p.PC_in + t0 - p.halo;  // first patch position (negative before the raster: zero fill)
-        for (int c = 0; c < nchunks; ++c, ++ca) {
-          const int st = ca % AS;
-          mbar_wait(smem_u32(&bars->a_empty[st]), ((ca / AS) & 1) ^ 1);
+        for (int c = 0; c < nchunks; ++c, ++a_ca) {
+          const int st = a_ca % AS;
+          mbar_wait(smem_u32(&bars->a_empty[st]), ((a_ca / AS) & 1) ^ 1);
           const uint32_t bar = smem_u32(&bars->a_full[st]);
           mbar_expect_tx(bar, (uint32_t)(nbox * box_rows * 128));
           for (int b = 0; b < nbox; ++b)
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(smem_u32(sA + st * a_stage + b * box_rows * 128)), "l"(reinterpret_cast<uint64_t>(&tmap)),
+                         ::"r"(smem_u32(sA + st * a_stage + b * box_rows * 128)), "l"(reinterpret_cast<uint64_t>(tm)),
                            "r"(c * 64), "r"(g0 + b * box_rows), "r"(bar) : "memory");
         }
       }
@@ -221,51 +247,55 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_kernel(const FlatConvPar
     const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
     const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
     constexpr int AK = 32 >> 4, BK = (2 * BN * 16) >> 4;
-    int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      const int acc = it & 1;
-      mbar_wait(smem_u32(&bars->acc_empty[acc]), ((it >> 1) & 1) ^ 1);
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++m_it) {
+      const int acc = m_it & 1;
+      mbar_wait(smem_u32(&bars->acc_empty[acc]), ((m_it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * FT * BN;
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(bar_a_full + sa * 8, pa);
+        mbar_wait(bar_a_full + m_sa * 8, m_pa);
         tc_fence_after();
-        const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + sa * (a_stage >> 4));
+        const uint64_t a_st = ((uint64_t)a_hi << 32) | (a_lo0 + m_sa * (a_stage >> 4));
 #pragma unroll 1
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          mbar_wait(bar_b_full + sb * 8, pb);
+          mbar_wait(bar_b_full + m_sb * 8, m_pb);
           tc_fence_after();
-          const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + sb * (B_STAGE >> 4));
+          const uint64_t b_st = ((uint64_t)b_hi << 32) | (b_lo0 + m_sb * (B_STAGE >> 4));
           const int a_off = (p.halo + p.shift[tap]) * 128;  // tap = shift of the patch start by whole positions
 #pragma unroll
           for (int tile = 0; tile < FT; ++tile)
             umma_tap<4, AK, BK>(tmem_acc + tile * BN, a_st + (uint64_t)((a_off + tile * 128 * 128) >> 4), b_st, idesc,
                                 (tap | c) ? 1u : 0u, leader);
-          umma_commit_if(bar_b_empty + sb * 8, leader);
-          if (++sb == BS) { sb = 0; pb ^= 1; }
+          umma_commit_if(bar_b_empty + m_sb * 8, leader);
+          if (++m_sb == BS) { m_sb = 0; m_pb ^= 1; }
         }
-        umma_commit_if(bar_a_empty + sa * 8, leader);
-        if (++sa == AS) { sa = 0; pa ^= 1; }
+        umma_commit_if(bar_a_empty + m_sa * 8, leader);
+        if (++m_sa == AS) { m_sa = 0; m_pa ^= 1; }
       }
       umma_commit_if(smem_u32(&bars->acc_full[acc]), leader);
     }
   } else {
     // =============================== weight producer: one 8 KB stage per (chunk, tap) ====================================
-    // Every CTA streams the SAME filter at the same time; `wrep` identical copies of it in global memory spread those
-    // simultaneous requests over different L2 lines (CTA i reads copy i % wrep).
     if (lane == 0) {
       const int per_item = nchunks * p.ntaps;
-      int sb = 0, pb = 1;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w + (size_t)(blockIdx.x % p.wrep) * p.wrep_stride);
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         for (int i = 0; i < per_item; ++i) {
-          mbar_wait(smem_u32(&bars->b_empty[sb]), pb);
-          mbar_expect_tx(smem_u32(&bars->b_full[sb]), B_STAGE);
-          bulk_g2s(smem_u32(sB + sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[sb]));
-          if (++sb == BS) { sb = 0; pb ^= 1; }
+          mbar_wait(smem_u32(&bars->b_empty[w_sb]), w_pb);
+          mbar_expect_tx(smem_u32(&bars->b_full[w_sb]), B_STAGE);
+          bulk_g2s(smem_u32(sB + w_sb * B_STAGE), src + (size_t)i * B_STAGE, B_STAGE, smem_u32(&bars->b_full[w_sb]));
+          if (++w_sb == BS) { w_sb = 0; w_pb ^= 1; }
         }
       }
     }
+  }
+  if (layer + 1 < P.nlayers) {
+    // the epilogues' global stores (generic proxy) must be visible to the TMA loads (async proxy) of every other CTA
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
   }
   tc_fence_before();
   __syncthreads();
@@ -349,12 +379,12 @@ int make_tmap2(const act_t* base, long long positions, int C, int box_rows, CUte
 
 }  // namespace
 
-FlatGeo flat_geo(int H, int W, int k, int G) {
+FlatGeo flat_geo(int H, int W, int k, int G, bool hgap) {
   FlatGeo g;
   g.p = (k - 1) / 2;
-  g.S = W + g.p;
+  g.S = W + (hgap ? g.p : 0);  // no gap after a row when the layer has no horizontal taps (first layer: they are channels)
   g.PI = (H + g.p) * g.S;
-  const long long need = (long long)G * g.PI + g.p;
+  const long long need = (long long)G * g.PI + (hgap ? g.p : 0);
   g.PC = (int)((need + ITEM_POS - 1) / ITEM_POS * ITEM_POS);
   return g;
 }
@@ -391,48 +421,70 @@ int launch_repack_flat(const float* w, act_t* out, int Cin, int k, cudaStream_t 
   return 0;
 }
 
-int launch_conv_flat(const FlatConvParams& p, cudaStream_t stream) {
-  if (p.Cin % 64 || p.ntaps < 1 || p.ntaps > 81 || p.halo > 64 || p.PC_in % ITEM_POS) { set_error("conv_flat: bad geometry"); return -1; }
-  const int np = ITEM_POS + 2 * p.halo;                       // patch positions of one work item
-  const int nbox = (np + 255) / 256;
-  const int box_rows = (((np + nbox - 1) / nbox) + 7) & ~7;   // every box starts on a 1024-byte swizzle atom
-  const int a_stage = nbox * box_rows * 128;
-  const int fixed = AS * a_stage + (((int)sizeof(FBarriers) + 15) & ~15) + 4 * BN * 4 + (BN * 8 + 8) * 4 + 64;
-  static const int env_bs = getenv("DYF_FLAT_BS") ? atoi(getenv("DYF_FLAT_BS")) : 0;
-  int BS = std::min(MAX_BS, (227 * 1024 - fixed) / B_STAGE);  // as deep as shared memory allows: the stream is latency-bound
-  if (env_bs >= 2 && env_bs < BS) BS = env_bs;
-  if (BS < 2) { set_error("conv_flat: patch too large for shared memory"); return -1; }
-  const int smem = fixed + BS * B_STAGE;
+int launch_conv_flat_net(const FlatConvParams* layers, int nlayers, cudaStream_t stream) {
+  if (nlayers < 1 || nlayers > FLAT_MAX_LAYERS) { set_error("conv_flat: 1..4 layers per launch"); return -1; }
   static int num_sms = 0, configured = 0;
   if (!num_sms) {
     int dev = 0;
     DYF_CUDA_OK(cudaGetDevice(&dev));
     DYF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (smem > configured) {
-    DYF_CUDA_OK(cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  FlatNetParams P{};
+  P.nlayers = nlayers;
+  CUtensorMap maps[FLAT_MAX_LAYERS]{};
+  int max_work = 0;
+  double flops = 0.0, bytes = 0.0;
   using Key = std::tuple<const void*, long long, int, int>;
   static std::map<Key, CUtensorMap> cache;
-  const long long positions = (long long)p.calls * p.PC_in;
-  const Key key{p.in, positions, p.Cin, box_rows};
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    CUtensorMap m;
-    if (make_tmap2(p.in, positions, p.Cin, box_rows, &m) != 0) { set_error("conv_flat: tensor map encoding failed"); return -1; }
-    if (cache.size() > 1024) cache.clear();
-    it = cache.emplace(key, m).first;
+  for (int l = 0; l < nlayers; ++l) {
+    const FlatConvParams& p = layers[l];
+    if (p.Cin % 64 || p.ntaps < 1 || p.ntaps > 81 || p.halo > 64 || p.PC_in % ITEM_POS) { set_error("conv_flat: bad geometry"); return -1; }
+    const int np = ITEM_POS + 2 * p.halo;                       // patch positions of one work item
+    const int nbox = (np + 255) / 256;
+    const int box_rows = (((np + nbox - 1) / nbox) + 7) & ~7;   // every box starts on a 1024-byte swizzle atom
+    P.a_stage = std::max(P.a_stage, nbox * box_rows * 128);
+    P.L[l] = p;
+    P.G[l].box_rows = box_rows; P.G[l].nbox = nbox;
+    P.G[l].items_per_call = p.PC_in / ITEM_POS;
+    P.G[l].num_work = p.calls * P.G[l].items_per_call;
+    max_work = std::max(max_work, P.G[l].num_work);
+    const long long positions = (long long)p.calls * p.PC_in;
+    const Key key{p.in, positions, p.Cin, box_rows};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      CUtensorMap m;
+      if (make_tmap2(p.in, positions, p.Cin, box_rows, &m) != 0) { set_error("conv_flat: tensor map encoding failed"); return -1; }
+      if (cache.size() > 1024) cache.clear();
+      it = cache.emplace(key, m).first;
+    }
+    maps[l] = it->second;
+    flops += 2.0 * (double)p.calls * p.G * p.H * p.W * BN * p.flops_k;
+    bytes += 2.0 * ((double)positions * p.Cin + (double)p.calls * p.G * p.H * p.W * BN) + 2.0 * p.ntaps * p.Cin * BN;
   }
-  const int items_per_call = p.PC_in / ITEM_POS;
-  const int num_work = p.calls * items_per_call;
-  const int grid = num_work < num_sms ? num_work : num_sms;
-  const double flops = 2.0 * (double)p.calls * p.G * p.H * p.W * BN * p.flops_k;
-  const double bytes = 2.0 * ((double)positions * p.Cin + (double)p.calls * p.G * p.H * p.W * BN) + 2.0 * p.ntaps * p.Cin * BN;
+  const int fixed = AS * P.a_stage + (((int)sizeof(FBarriers) + 15) & ~15) + 4 * BN * 4 + (BN * 8 + 8) * 4 + 64;
+  static const int env_bs = getenv("DYF_FLAT_BS") ? atoi(getenv("DYF_FLAT_BS")) : 0;
+  int BS = std::min(MAX_BS, (227 * 1024 - fixed) / B_STAGE);
+  if (env_bs >= 2 && env_bs < BS) BS = env_bs;
+  if (BS < 2) { set_error("conv_flat: patch too large for shared memory"); return -1; }
+  P.BS = BS;
+  const int smem = fixed + BS * B_STAGE;
+  if (smem > configured) {
+    DYF_CUDA_OK(cudaFuncSetAttribute(conv_flat_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int grid = max_work < num_sms ? max_work : num_sms;
   ProfScope prof(stream, KC_CONV_FLAT, flops, bytes);
-  conv_flat_kernel<<<grid, THREADS, smem, stream>>>(p, it->second, a_stage, box_rows, nbox, num_work, items_per_call, BS);
-  DYF_LAUNCH_OK("conv_flat_kernel");
+  if (nlayers == 1) {
+    conv_flat_net_kernel<<<grid, THREADS, smem, stream>>>(P, maps[0], maps[1], maps[2], maps[3]);
+  } else {  // grid-wide barriers between the layers: cooperative launch (one CTA per SM, all co-resident)
+    void* args[] = {&P, &maps[0], &maps[1], &maps[2], &maps[3]};
+    DYF_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv_flat_net_kernel), dim3(grid), dim3(THREADS), args,
+                                            (size_t)smem, stream));
+  }
+  DYF_LAUNCH_OK("conv_flat_net_kernel");
   return 0;
 }
+
+int launch_conv_flat(const FlatConvParams& p, cudaStream_t stream) { return launch_conv_flat_net(&p, 1, stream); }
 
 }  // namespace dyf

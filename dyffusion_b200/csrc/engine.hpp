@@ -73,7 +73,7 @@ struct Buf {
 };
 
 struct LNLayer { int g = -1; int C = 0; };
-struct FlatBuf { int k = 1, C = 64; };  // raster read by a k x k layer, C channels per position (conv_flat.cu)  // channel LayerNorm (gain only) in front of an attention block
+struct FlatBuf { int k = 1, C = 64; bool hgap = true; };  // raster read by a k x k layer, C channels per position (conv_flat.cu)  // channel LayerNorm (gain only) in front of an attention block
 
 struct Net {
   dyf_net_desc d{};

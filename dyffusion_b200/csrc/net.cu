@@ -324,7 +324,7 @@ int Net::build_convnet() {
     const int k0 = d.kernel_sizes[0], cp = round_up(cin, 8), cflat = round_up(k0 * cp, 64);
     flat = cin <= 16 && cflat <= 256 && (k0 - 1) / 2 * (Win + (k0 - 1) / 2) <= 64;
     if (flat) {
-      FlatBuf fb; fb.k = k0; fb.C = cflat;
+      FlatBuf fb; fb.k = k0; fb.C = cflat; fb.hgap = false;  // horizontal taps live in the channel axis
       flats.push_back(fb);
       Op pk{}; pk.type = OP_FLAT_PACK; pk.out = 0;
       ops.push_back(pk);
@@ -719,7 +719,7 @@ int Net::ensure_flat(int G, int calls, cudaStream_t s) {
   size_t total = 0;
   for (size_t i = 0; i < flats.size(); ++i) {
     offs[i] = total;
-    const FlatGeo g = flat_geo(d.height, d.width, flats[i].k, G);
+    const FlatGeo g = flat_geo(d.height, d.width, flats[i].k, G, flats[i].hgap);
     total += ((size_t)cap * g.PC * flats[i].C * sizeof(act_t) + 1023) & ~(size_t)1023;
   }
   if (total > flat_bytes) {
@@ -829,7 +829,45 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
     }
   }
 
-  for (const Op& o : ops) {
+  static const bool flat_persist = !(getenv("DYF_FLAT_PERSIST") && getenv("DYF_FLAT_PERSIST")[0] == '0');
+  // parameters of one flat-raster layer (conv_flat.cu)
+  auto flat_params = [&](const Op& o) {
+    const ConvLayer& c = convs[o.layer];
+    const int G = group_rows, calls = rows / group_rows, k = c.KH, pad = (k - 1) / 2;
+    const FlatGeo gi = flat_geo(d.height, d.width, k, G, flats[o.in0].hgap);
+    FlatConvParams p{};
+    p.in = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.in0]);
+    p.w = wq_umma + c.flat_off; p.wrep = flat_weight_replicas(); p.wrep_stride = c.flat_elems;
+    p.H = d.height; p.W = d.width; p.G = G; p.calls = calls;
+    p.S_in = gi.S; p.PI_in = gi.PI; p.PC_in = gi.PC;
+    if (o.aux) {  // last layer: plain NHWC [rows][H][W][64]
+      p.out = bp[o.out]; p.S_out = d.width; p.PI_out = d.height * d.width; p.PC_out = G * p.PI_out;
+      if (o.aux == 2) {  // ... or straight to the network output through the fused 1x1 head
+        const ConvLayer& hc = convs[o.c0];
+        p.head_w = packed + params[hc.w].off; p.head_b = packed + params[hc.b].off; p.head_out = y; p.head_oc = d.out_channels;
+      }
+    } else {
+      const FlatGeo go = flat_geo(d.height, d.width, flats[o.out].k, G, flats[o.out].hgap);
+      p.out = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.out]);
+      p.S_out = go.S; p.PI_out = go.PI; p.PC_out = go.PC;
+    }
+    p.res = o.res >= 0 ? p.in : nullptr;
+    p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
+    p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
+    p.Cin = c.flat_cin;
+    if (c.flat_first) {  // horizontal taps live in the channel axis: k vertical taps
+      p.ntaps = k; p.halo = pad * gi.S;
+      for (int ky = 0; ky < k; ++ky) p.shift[ky] = (ky - pad) * gi.S;
+    } else {
+      p.ntaps = k * k; p.halo = pad * gi.S + pad;
+      for (int t = 0; t < k * k; ++t) p.shift[t] = (t / k - pad) * gi.S + (t % k - pad);
+    }
+    p.act = o.act; p.flops_k = (double)c.Cin * k * k;
+    p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
+    return p;
+  };
+  for (size_t oi = 0; oi < ops.size(); ++oi) {
+    const Op& o = ops[oi];
     int rc = 0;
     switch (o.type) {
       case OP_STEM: {
@@ -993,7 +1031,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         rc = ensure_flat(G, calls, s);
         if (rc) break;
         const ConvLayer& c0 = convs[ops[1].layer];
-        const FlatGeo g = flat_geo(d.height, d.width, flats[0].k, G);
+        const FlatGeo g = flat_geo(d.height, d.width, flats[0].k, G, flats[0].hgap);
         FlatPackParams p{};
         const long long plane = (long long)d.height * d.width;
         for (int i = 0; i < nsrc; ++i)
@@ -1010,39 +1048,15 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         break;
       }
       case OP_FLAT_CONV: {
-        const ConvLayer& c = convs[o.layer];
-        const int G = group_rows, calls = rows / group_rows, k = c.KH, pad = (k - 1) / 2;
-        const FlatGeo gi = flat_geo(d.height, d.width, k, G);
-        FlatConvParams p{};
-        p.in = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.in0]);
-        p.w = wq_umma + c.flat_off; p.wrep = flat_weight_replicas(); p.wrep_stride = c.flat_elems;
-        p.H = d.height; p.W = d.width; p.G = G; p.calls = calls;
-        p.S_in = gi.S; p.PI_in = gi.PI; p.PC_in = gi.PC;
-        if (o.aux) {  // last layer: plain NHWC [rows][H][W][64]
-          p.out = bp[o.out]; p.S_out = d.width; p.PI_out = d.height * d.width; p.PC_out = G * p.PI_out;
-          if (o.aux == 2) {  // ... or straight to the network output through the fused 1x1 head
-            const ConvLayer& hc = convs[o.c0];
-            p.head_w = packed + params[hc.w].off; p.head_b = packed + params[hc.b].off; p.head_out = y; p.head_oc = d.out_channels;
-          }
-        } else {
-          const FlatGeo go = flat_geo(d.height, d.width, flats[o.out].k, G);
-          p.out = reinterpret_cast<act_t*>(reinterpret_cast<uint8_t*>(flat_mem) + flat_offs[o.out]);
-          p.S_out = go.S; p.PI_out = go.PI; p.PC_out = go.PC;
+        // consecutive flat layers of the network run in ONE persistent kernel (grid-wide barriers between them)
+        FlatConvParams lp[FLAT_MAX_LAYERS];
+        int nl = 0;
+        while (nl < (flat_persist ? FLAT_MAX_LAYERS : 1) && oi + nl < ops.size() && ops[oi + nl].type == OP_FLAT_CONV) {
+          lp[nl] = flat_params(ops[oi + nl]);
+          ++nl;
         }
-        p.res = o.res >= 0 ? p.in : nullptr;
-        p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
-        p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
-        p.Cin = c.flat_cin;
-        if (c.flat_first) {  // horizontal taps live in the channel axis: k vertical taps
-          p.ntaps = k; p.halo = pad * gi.S;
-          for (int ky = 0; ky < k; ++ky) p.shift[ky] = (ky - pad) * gi.S;
-        } else {
-          p.ntaps = k * k; p.halo = pad * gi.S + pad;
-          for (int t = 0; t < k * k; ++t) p.shift[t] = (t / k - pad) * gi.S + (t % k - pad);
-        }
-        p.act = o.act; p.flops_k = (double)c.Cin * k * k;
-        p.drop = make_drop(rng, (uint32_t)o.site, o.drop_p);
-        rc = launch_conv_flat(p, s);
+        rc = launch_conv_flat_net(lp, nl, s);
+        oi += nl - 1;
         break;
       }
       default: set_error("internal: unknown op"); return DYF_ERR_STATE;
