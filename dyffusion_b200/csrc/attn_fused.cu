@@ -630,9 +630,10 @@ int launch_attention_mma(const AttnParams& p, cudaStream_t s) {
   return rc ? rc : 1;
 }
 
-int linattn_fused_chunks(int n) { return std::max(1, std::min(8, (n + 511) / 512)); }
-// per row: the chunk partials (fp32) followed by the combined 16-bit context [4][32][32]
-size_t linattn_fused_scratch_floats(int n) { return (size_t)linattn_fused_chunks(n) * HEADS * PART + HEADS * DH * DH / 2; }
+// pixel chunks per row of pass 1 (a partial per chunk): one 128-pixel tile each, at most 8.  The chunking depends on the grid
+// only -- never on the row count -- so a rank of a sharded job computes bit for bit what the full batch computes.
+int linattn_fused_chunks(int n) { return std::max(1, std::min(8, (n + TP - 1) / TP)); }
+size_t linattn_fused_scratch_floats(int) { return (size_t)8 * HEADS * PART + HEADS * DH * DH / 2; }
 bool linattn_fused_shape_ok(int C, int heads) { return heads == HEADS && (C == 64 || C == 128 || C == 256); }
 
 int launch_linattn_fused(const LinAttnFusedParams& p0, cudaStream_t s) {

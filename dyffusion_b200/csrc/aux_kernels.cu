@@ -475,64 +475,79 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const GroupNormPar
 // shared memory (rank order: bit-reproducible); second pass: y = act(x * A + B) -> dropout -> + residual.  The slice
 // (<= 64 KB) was just streamed by the same CTA, so the second read hits L2: DRAM traffic is one read and one write of the
 // tensor instead of two reads and one write, and one launch replaces three.
-constexpr int GNF_THREADS = 256, GNF_UNROLL = 4;
-__global__ void __launch_bounds__(GNF_THREADS, 4) groupnorm_fused_kernel(const GroupNormParams p, int CS, int pix_per_cta) {
+constexpr int GNF_THREADS = 256, GNF_UNROLL = 4, GNF_SLABS = 8;
+#ifndef GNF_MINB
+#define GNF_MINB 8
+#endif
+#ifndef GNF_AU
+#define GNF_AU 1
+#endif
+__global__ void __launch_bounds__(GNF_THREADS, GNF_MINB) groupnorm_fused_kernel(const GroupNormParams p, int CS, int slab_pix) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float s_part[GNF_THREADS][2];
-  __shared__ float s_sum[64][2];   // this CTA's per-group partial sums (read by the other CTAs of the cluster)
-  __shared__ float s_grp[64][2];   // mean, rstd
+  __shared__ float s_sum[GNF_SLABS][64][2];  // per-group partial sums of this CTA's slabs (read by the whole cluster)
+  __shared__ float s_grp[64][2];             // mean, rstd
   extern __shared__ __align__(16) float s_ab[];  // [2][C]
   const int r = blockIdx.x / CS, rank = blockIdx.x - r * CS;
   const int chunks = p.C >> 3, cpg = p.C / p.G;
   const int ch = threadIdx.x % chunks, lane_px = threadIdx.x / chunks, pstep = GNF_THREADS / chunks;
-  const int p_beg = rank * pix_per_cta, p_end = min(p.HW, p_beg + pix_per_cta);
+  // The row is cut into GNF_SLABS fixed pixel slabs whatever the cluster size; a CTA owns GNF_SLABS / CS consecutive slabs,
+  // reduces each one separately, and the row totals are the slab sums added in slab order: the statistics (and with them
+  // every output bit) do not depend on how many CTAs share a row -- a rank of a sharded job computes what the full batch does.
+  const int spc = GNF_SLABS / CS;  // slabs per CTA
+  const int p_beg = rank * spc * slab_pix, p_end = min(p.HW, p_beg + spc * slab_pix);
   const act_t* x = p.x + (size_t)r * p.HW * p.C + (ch << 3);
-  float s1 = 0.f, s2 = 0.f;
-  int px = p_beg + lane_px;
-  for (; px + (GNF_UNROLL - 1) * pstep < p_end; px += GNF_UNROLL * pstep) {
-    uint4 u[GNF_UNROLL];
+  int px;
+  for (int sl = 0; sl < spc; ++sl) {
+    const int s_beg = p_beg + sl * slab_pix, s_end = min(p.HW, s_beg + slab_pix);
+    float s1 = 0.f, s2 = 0.f;
+    px = s_beg + lane_px;
+    for (; px + (GNF_UNROLL - 1) * pstep < s_end; px += GNF_UNROLL * pstep) {
+      uint4 u[GNF_UNROLL];
 #pragma unroll
-    for (int k = 0; k < GNF_UNROLL; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(px + k * pstep) * p.C));
+      for (int k = 0; k < GNF_UNROLL; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(px + k * pstep) * p.C));
 #pragma unroll
-    for (int k = 0; k < GNF_UNROLL; ++k) {
+      for (int k = 0; k < GNF_UNROLL; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
+      }
+    }
+    for (; px < s_end; px += pstep) {
       float f[8];
-      unpack8(u[k], f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)px * p.C)), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
     }
-  }
-  for (; px < p_end; px += pstep) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)px * p.C)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 += f[j] * f[j]; }
-  }
-  s_part[threadIdx.x][0] = s1;
-  s_part[threadIdx.x][1] = s2;
-  __syncthreads();
-  for (int half = pstep >> 1; half > 0; half >>= 1) {  // tree over the pixel lanes of every chunk (pstep is a power of two)
-    if ((int)threadIdx.x < half * chunks) {
-      s_part[threadIdx.x][0] += s_part[threadIdx.x + half * chunks][0];
-      s_part[threadIdx.x][1] += s_part[threadIdx.x + half * chunks][1];
-    }
+    s_part[threadIdx.x][0] = s1;
+    s_part[threadIdx.x][1] = s2;
     __syncthreads();
+    for (int half = pstep >> 1; half > 0; half >>= 1) {  // tree over the pixel lanes of every chunk (pstep is a power of two)
+      if ((int)threadIdx.x < half * chunks) {
+        s_part[threadIdx.x][0] += s_part[threadIdx.x + half * chunks][0];
+        s_part[threadIdx.x][1] += s_part[threadIdx.x + half * chunks][1];
+      }
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < p.G) {  // chunks of a group in index order
+      const int g = threadIdx.x, cpc = cpg >> 3;
+      float a = 0.f, b = 0.f;
+      for (int c = g * cpc; c < (g + 1) * cpc; ++c) { a += s_part[c][0]; b += s_part[c][1]; }
+      s_sum[sl][g][0] = a;
+      s_sum[sl][g][1] = b;
+    }
+    __syncthreads();  // s_part is rewritten by the next slab
   }
-  if ((int)threadIdx.x < p.G) {  // chunks of a group in index order
-    const int g = threadIdx.x, cpc = cpg >> 3;
-    float a = 0.f, b = 0.f;
-    for (int c = g * cpc; c < (g + 1) * cpc; ++c) { a += s_part[c][0]; b += s_part[c][1]; }
-    s_sum[g][0] = a;
-    s_sum[g][1] = b;
-  }
-  cluster.sync();  // every CTA's partial sums are in place (also a CTA barrier)
+  cluster.sync();  // every CTA's slab sums are in place
   if ((int)threadIdx.x < p.G) {
     const int g = threadIdx.x;
     float a = 0.f, b = 0.f;
-    for (int k = 0; k < CS; ++k) {  // rank order
-      const float* remote = cluster.map_shared_rank(&s_sum[0][0], k);
-      a += remote[2 * g];
-      b += remote[2 * g + 1];
+    for (int sl = 0; sl < GNF_SLABS; ++sl) {  // slab order, whatever CTA holds the slab
+      const float* remote = cluster.map_shared_rank(&s_sum[0][0][0], sl / spc);
+      a += remote[((sl % spc) * 64 + g) * 2];
+      b += remote[((sl % spc) * 64 + g) * 2 + 1];
     }
     const float n = (float)p.HW * (float)cpg;
     const float mean = a / n;
@@ -559,7 +574,7 @@ __global__ void __launch_bounds__(GNF_THREADS, 4) groupnorm_fused_kernel(const G
   const DropRow dr = drop_row(p.drop, r, (uint64_t)p.HW * p.C);
   act_t* y = p.y + (size_t)r * p.HW * p.C + (ch << 3);
   const act_t* res = p.res ? p.res + (size_t)r * p.HW * p.res_ld + (ch << 3) : nullptr;
-  constexpr int AU = 2;  // pixels in flight per thread in the apply pass
+  constexpr int AU = GNF_AU;  // pixels in flight per thread in the apply pass
   for (px = p_beg + lane_px; px < p_end; px += AU * pstep) {
     uint4 u[AU], rr[AU];
 #pragma unroll
@@ -1013,8 +1028,11 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
     const size_t row_bytes = (size_t)p.HW * p.C * sizeof(act_t);
     int CS = 1;
     while (CS < 8 && row_bytes / CS > (64u << 10)) CS *= 2;
+    // few rows (a rank of a sharded job): more CTAs per row, so that the two dependent passes of a CTA are short and at least
+    // two CTAs per SM are in flight
+    while (CS < 8 && (long long)p.rows * CS < 2 * 148 && row_bytes / CS > (8u << 10)) CS *= 2;
     const int pstep = GNF_THREADS / chunks;
-    const int per = cdiv(cdiv(p.HW, CS), pstep) * pstep;  // pixels per CTA (whole pixel-lane rounds)
+    const int per = cdiv(cdiv(p.HW, GNF_SLABS), pstep) * pstep;  // pixels per slab (whole pixel-lane rounds), independent of CS
     ProfScope prof(s, KC_GROUPNORM);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.rows * CS)); cfg.blockDim = dim3(GNF_THREADS);

@@ -3,7 +3,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
 recs = [(r[ix["Kernel Name"]], float(r[ix["Metric Value"]].replace(",", ""))) for r in rows[hi + 1:] if len(r) >= len(hdr)]
-starts = [k for k, (n, _) in enumerate(recs) if "pack_kernel" in n]
+starts = [k for k, (n, _) in enumerate(recs) if "pack_" in n or "pack_kernel" in n]
 fw = recs[starts[-1]:]
 agg = collections.OrderedDict()
 for n, t in fw:
