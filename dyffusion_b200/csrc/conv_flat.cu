@@ -35,7 +35,7 @@ namespace {
 
 constexpr int FT = 2;                       // M tiles (128 positions each) per work item
 constexpr int ITEM_POS = 128 * FT;          // positions per work item
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;                // 2 per TMEM lane quarter (16 were measured: no gain, the MMA side is the limiter)
 constexpr int THREADS = (EPI_WARPS + 3) * 32;
 constexpr int BN = 64;
 constexpr int B_STAGE = BN * 64 * 2;        // one tap of one 64-channel chunk: [k8][64][8] = 8 KB
@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
     // Plain layers: warp = (TMEM lane quarter, column half), both tiles.  Last layer with the 1x1 head fused in
     // (head_out != nullptr): warp = (lane quarter, tile), all 64 columns, so that one thread owns a whole pixel and the
     // head's C_out dot products (fp32 activations x fp32 weights) need no cross-warp reduction; the 64-channel map is
-    // then never written.
+    // then never written.  (A 16-warp variant -- one 128 x 32 unit per warp -- was measured: no gain.)
     const bool fused_head = p.head_out != nullptr;
-    const int quarter = warp & 3, hi = warp >> 2;
+    const int quarter = warp & 3, sub4 = warp >> 2;
     const uint32_t thresh = p.drop.thresh;
     const float dscale = p.drop.scale;
     float* const sHead = sTab + 4 * BN;  // [64][8] head weights (channel-major), [8] bias
@@ -128,16 +128,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
       const float* const tab = sTab + tab_buf * 2 * BN;
-      // units of work of this warp: (tile, first column) pairs -- 2 tiles x its column half, or its tile x 2 column halves
+      // units of work of this warp: (tile, first column) pairs
       int u_tile[2], u_col[2];
-      u_tile[0] = fused_head ? hi : 0; u_tile[1] = fused_head ? hi : 1;
-      u_col[0] = fused_head ? 0 : hi * 32; u_col[1] = fused_head ? 32 : hi * 32;
+      int nu;
+      if constexpr (EPI_WARPS == 8) {  // warp = (quarter, column half) x both tiles, or (quarter, tile) x both halves
+        nu = 2;
+        u_tile[0] = fused_head ? sub4 : 0; u_tile[1] = fused_head ? sub4 : 1;
+        u_col[0] = fused_head ? 0 : sub4 * 32; u_col[1] = fused_head ? 32 : sub4 * 32;
+      } else {                         // 16 warps: one unit each; the fused head uses warps 0-7 with two units
+        nu = fused_head ? (sub4 < 2 ? 2 : 0) : 1;
+        u_tile[0] = fused_head ? (sub4 & 1) : (sub4 >> 1); u_tile[1] = u_tile[0];
+        u_col[0] = fused_head ? 0 : (sub4 & 1) * 32; u_col[1] = 32;
+      }
       // geometry + residual of both units before the accumulator is waited for: their latency hides behind the MMAs
       int lp[2], img[2], yy[2], xx[2];
       bool valid[2];
       uint4 rsd[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
+        if (u >= nu) { valid[u] = false; continue; }
         lp[u] = t0 + u_tile[u] * 128 + quarter * 32 + lane;
         img[u] = lp[u] / p.PI_in;
         const int rem = lp[u] - img[u] * p.PI_in;
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
       float hacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
+        if (u >= nu) break;  // (warp-uniform)
         const int cbeg = u_col[u];
         uint32_t v[32];
         tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * FT + u_tile[u]) * BN + cbeg, v);
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
         }
         __syncwarp();  // the next tcgen05.ld is warp-collective
       }
-      if (fused_head && valid[0]) {  // fp32 NCHW network output [rows][C_out][H][W]
+      if (fused_head && nu && valid[0]) {  // fp32 NCHW network output [rows][C_out][H][W]
         const int HW = p.H * p.W;
         float* const op = p.head_out + (size_t)(call * p.G + img[0]) * p.head_oc * HW + yy[0] * p.W + xx[0];
 #pragma unroll

@@ -186,13 +186,16 @@ def _require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 class _Workspace:
-    """Grow-only per-device scratch owned by torch's caching allocator."""
+    """Grow-only scratch per (device, CUDA stream), owned by torch's caching allocator: engine calls enqueued on different
+    streams never share a workspace (the epilogue-table cache of a net is still per net: issue a net's first call for a
+    new time tuple on one stream before using it from others)."""
 
     def __init__(self):
-        self.buf: Dict[int, torch.Tensor] = {}
+        self.buf: Dict[Tuple[int, int], torch.Tensor] = {}
 
     def get(self, nbytes: int, device: torch.device) -> torch.Tensor:
-        key = device.index if device.index is not None else torch.cuda.current_device()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, int(torch.cuda.current_stream(idx).cuda_stream))
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             self.buf[key] = b = None  # release before growing
