@@ -97,10 +97,11 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s);
 // 64 -> 16 * Cout (z[pixel][(ky*4+kx)*Cout + co] = sum_ci x[pixel][ci] * Wt[ci][co][ky][kx]); this kernel then gathers, for
 // every output pixel, the 2x2 bilinear corners x 2x2 valid taps from z and adds the bias.
 struct ReadoutGatherParams {
-  const act_t* z;  // [rows, Hs, Ws, 16 * Cout]
+  const act_t* z;  // [rows, Hs, Wz, 16 * Cout]
   const float* bias;       // [Cout]
   float* y;                // [rows, Cout, Ho, Wo]
-  int rows, Hs, Ws, Cout, Ho, Wo;
+  const int* xinv;         // optional: source column -> column of z (z holds only the source columns the resize samples)
+  int rows, Hs, Ws, Wz, Cout, Ho, Wo;  // Ws = source grid width, Wz = columns stored in z (= Ws without xinv)
 };
 int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s);
 // ConvTranspose2d weight fp32 [Cin, Cout, 4, 4] -> 1x1-conv weight [16 * Cout, Cin] (row (ky*4+kx)*Cout + co)

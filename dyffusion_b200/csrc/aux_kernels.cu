@@ -25,14 +25,25 @@ __device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b) {
   return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
 }
 
+// Movers index their work as (batch row, position inside the row) over grids of rows x ceil(per_row / 256) blocks, so
+// the per-thread index arithmetic stays 32-bit: a 64-bit division by a run-time value is ~100 instructions per thread,
+// which made these copy kernels issue-bound (pack_s2d: 535 instructions per 32 output bytes).
+struct RowPos { unsigned r, i; };
+__device__ __forceinline__ RowPos row_pos(unsigned per_row) {
+  const unsigned bpr = (per_row + 255u) >> 8;
+  const unsigned r = blockIdx.x / bpr;
+  return {r, (blockIdx.x - r * bpr) * 256u + threadIdx.x};
+}
+static inline unsigned row_grid(long long rows, long long per_row) { return (unsigned)(rows * ((per_row + 255) / 256)); }
+
 // ------------------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
-  const long long total = (long long)p.rows * p.Ho * p.Wo;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = (int)(idx % p.Wo);
-  const int oy = (int)((idx / p.Wo) % p.Ho);
-  const int r = (int)(idx / ((long long)p.Wo * p.Ho));
+  const unsigned per_row = (unsigned)(p.Ho * p.Wo);
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const int oy = (int)(rp.i / (unsigned)p.Wo), ox = (int)(rp.i - (unsigned)oy * p.Wo);
+  const int r = (int)rp.r;
+  const size_t idx = (size_t)rp.r * per_row + rp.i;
   int y0 = oy, y1 = oy, x0 = ox, x1 = ox;
   float ly = 0.f, lx = 0.f;
   if (p.bilinear) {
@@ -41,7 +52,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
   }
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const size_t plane = (size_t)p.Hi * p.Wi;
-  act_t* o = p.out + (size_t)idx * p.Cpad;
+  act_t* o = p.out + idx * p.Cpad;
   float v[8];
   int oc = 0;
   for (int s = 0; s < p.nsrc; ++s) {
@@ -82,15 +93,15 @@ struct S2dChannels {
   int row_stride[16];      // floats between consecutive source rows of that tensor
   int n;                   // real channels (slot n carries 1.0)
 };
+template <int N>  // N = real channels (compile time: the 4 N gathers of a thread are all in flight before the first use)
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const S2dChannels ch) {
-  const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int sub = (int)(idx & 3);
-  const long long blk = idx >> 2;
-  const int bx = (int)(blk % p.Wo);
-  const int by = (int)((blk / p.Wo) % p.Ho);
-  const int r = (int)(blk / ((long long)p.Wo * p.Ho));
+  const unsigned per_row = (unsigned)(p.Ho * p.Wo) * 4u;
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const int sub = (int)(rp.i & 3u);
+  const unsigned pb = rp.i >> 2;  // block pixel inside the row
+  const int by = (int)(pb / (unsigned)p.Wo), bx = (int)(pb - (unsigned)by * p.Wo);
+  const size_t blk = (size_t)rp.r * (per_row >> 2) + pb;
   const int oy = 2 * by + (sub >> 1), ox = 2 * bx + (sub & 1);  // pixel of the full (resized) grid
   const int Hf = 2 * p.Ho, Wf = 2 * p.Wo;
   int y0 = oy, y1 = oy, x0 = ox, x1 = ox;
@@ -101,19 +112,18 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const
   }
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const int o00 = y0 * p.Wi + x0, o01 = y0 * p.Wi + x1, o10 = y1 * p.Wi + x0, o11 = y1 * p.Wi + x1;
-  const int rs = r % p.src_rows;
+  const unsigned rs = rp.r % (unsigned)p.src_rows;  // block-uniform
+  float g[N][4];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float* pl = ch.plane[i] + (size_t)rs * ch.row_stride[i];
+    g[i][0] = __ldg(pl + o00); g[i][1] = __ldg(pl + o01); g[i][2] = __ldg(pl + o10); g[i][3] = __ldg(pl + o11);
+  }
   float v[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {  // compile-time slot index: all gathers are issued before any is consumed
-    float val = i == ch.n ? 1.f : 0.f;
-    if (i < ch.n) {
-      const float* pl = ch.plane[i] + (size_t)rs * ch.row_stride[i];
-      val = p.bilinear ? w00 * __ldg(pl + o00) + w01 * __ldg(pl + o01) + w10 * __ldg(pl + o10) + w11 * __ldg(pl + o11)
-                       : __ldg(pl + o00);
-    }
-    v[i] = val;
-  }
-  uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)blk * 64 + sub * 16);
+  for (int i = 0; i < 16; ++i)
+    v[i] = i < N ? (w00 * g[i][0] + w01 * g[i][1] + w10 * g[i][2] + w11 * g[i][3]) : i == N ? 1.f : 0.f;
+  uint4* o = reinterpret_cast<uint4*>(p.out + blk * 64 + sub * 16);
   o[0] = pack8(v);
   o[1] = pack8(v + 8);
 }
@@ -124,15 +134,14 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const
 // seven VERTICAL taps over 64 channels on the tcgen05 halo-patch kernel (conv_umma.cu, S1K7V).  "data+noise" conditioning is
 // applied per source element with the element-keyed Philox stream of pack_kernel (the seven copies of a pixel agree).
 __global__ void __launch_bounds__(256) pack_xim2col_kernel(const PackParams p, const S2dChannels ch) {
-  const long long total = (long long)p.rows * p.Ho * p.Wo;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int x = (int)(idx % p.Wo);
-  const int y = (int)((idx / p.Wo) % p.Ho);
-  const int r = (int)(idx / ((long long)p.Wo * p.Ho));
+  const unsigned per_row = (unsigned)(p.Ho * p.Wo);
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const int y = (int)(rp.i / (unsigned)p.Wo), x = (int)(rp.i - (unsigned)y * p.Wo);
+  const int r = (int)rp.r;
   const int rs = r % p.src_rows;
   const size_t plane = (size_t)p.Hi * p.Wi;
-  uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)idx * 64);
+  uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)rp.r * per_row + rp.i) * 64);
 #pragma unroll
   for (int kx = 0; kx < 7; ++kx) {
     const int xs = x + kx - 3;
@@ -274,14 +283,14 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
   const int Ho = p.H * p.scale, Wo = p.W * p.scale;
   const int Ct = p.C[0] + p.C[1];
   const int chunks = Ct >> 3;
-  const long long total = (long long)p.rows * Ho * Wo * chunks;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ch = (int)(idx % chunks);
-  const long long pix = idx / chunks;
-  const int ox = (int)(pix % Wo);
-  const int oy = (int)((pix / Wo) % Ho);
-  const int r = (int)(pix / ((long long)Wo * Ho));
+  const unsigned per_row = (unsigned)(Ho * Wo * chunks);
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const unsigned pr = rp.i / (unsigned)chunks;  // pixel inside the row
+  const int ch = (int)(rp.i - pr * chunks);
+  const int oy = (int)(pr / (unsigned)Wo), ox = (int)(pr - (unsigned)oy * Wo);
+  const int r = (int)rp.r;
+  const size_t pix = (size_t)rp.r * ((size_t)Ho * Wo) + pr;
   const int c = ch << 3;
   const int s = c < p.C[0] ? 0 : 1;
   const int cs = s ? c - p.C[0] : c;
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
     for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * b[j] + w10 * cc[j] + w11 * d[j];
     outv = pack8(o);
   }
-  *reinterpret_cast<uint4*>(p.out + (size_t)pix * Ct + c) = outv;
+  *reinterpret_cast<uint4*>(p.out + pix * Ct + c) = outv;
 }
 
 // Bilinear x2 (align_corners=False) as a fixed separable stencil: with source indices clamped to the image,
@@ -316,14 +325,13 @@ __global__ void __launch_bounds__(256) upsample_kernel(const UpsampleParams p) {
 __global__ void __launch_bounds__(256) upsample2x_quad_kernel(const UpsampleParams p) {
   const int Ct = p.C[0] + p.C[1];
   const int chunks = Ct >> 3;
-  const long long total = (long long)p.rows * p.H * p.W * chunks;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ch = (int)(idx % chunks);
-  const long long pix = idx / chunks;
-  const int j = (int)(pix % p.W);
-  const int i = (int)((pix / p.W) % p.H);
-  const int r = (int)(pix / ((long long)p.W * p.H));
+  const unsigned per_row = (unsigned)(p.H * p.W * chunks);
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const unsigned pr = rp.i / (unsigned)chunks;  // source pixel inside the row
+  const int ch = (int)(rp.i - pr * chunks);
+  const int i = (int)(pr / (unsigned)p.W), j = (int)(pr - (unsigned)i * p.W);
+  const int r = (int)rp.r;
   const int c = ch << 3;
   const int s = c < p.C[0] ? 0 : 1;
   const int cs = s ? c - p.C[0] : c;
@@ -681,37 +689,56 @@ __global__ void __launch_bounds__(256) readout_kernel(const ReadoutParams p) {
 
 // readout, step 2: gather (one thread per output pixel and channel)
 __global__ void __launch_bounds__(256) readout_gather_kernel(const ReadoutGatherParams p) {
-  const long long total = (long long)p.rows * p.Ho * p.Wo * p.Cout;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int co = (int)(idx % p.Cout);
-  const long long pix = idx / p.Cout;
-  const int ox = (int)(pix % p.Wo);
-  const int oy = (int)((pix / p.Wo) % p.Ho);
-  const int r = (int)(pix / ((long long)p.Wo * p.Ho));
+  const unsigned per_row = (unsigned)(p.Ho * p.Wo * p.Cout);
+  const RowPos rp = row_pos(per_row);
+  if (rp.i >= per_row) return;
+  const unsigned pr = rp.i / (unsigned)p.Cout;  // output pixel inside the row
+  const int co = (int)(rp.i - pr * p.Cout);
+  const int oy = (int)(pr / (unsigned)p.Wo), ox = (int)(pr - (unsigned)oy * p.Wo);
+  const int r = (int)rp.r;
   const int H2 = 2 * p.Hs, W2 = 2 * p.Ws, ldz = 16 * p.Cout;
   int Y[2], X[2];
   float ly, lx;
   bilinear_coord(oy, H2, (float)H2 / (float)p.Ho, Y[0], Y[1], ly);
   bilinear_coord(ox, W2, (float)W2 / (float)p.Wo, X[0], X[1], lx);
   const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
-  const act_t* zr = p.z + (size_t)r * p.Hs * p.Ws * ldz + co;
+  const act_t* zr = p.z + (size_t)r * p.Hs * p.Wz * ldz + co;
+  // 2 x 2 bilinear corners x 2 x 2 transposed-conv taps: the 16 addresses are formed first (clamped, invalid taps masked
+  // afterwards) so that the 16 loads of a thread are in flight together
+  int rowo[2][2], colo[2][2];  // [corner][tap]: element offset of the source row / of (column, tap channel)
+  bool rok[2][2], cok[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+      const int ky = ((Y[a] + 1) & 1) + 2 * dd, iy = (Y[a] + 1 - ky) >> 1;
+      rok[a][dd] = iy >= 0 && iy < p.Hs;
+      rowo[a][dd] = min(max(iy, 0), p.Hs - 1) * p.Wz * ldz + ky * 4 * p.Cout;
+      const int kx = ((X[a] + 1) & 1) + 2 * dd, ix = (X[a] + 1 - kx) >> 1;
+      cok[a][dd] = ix >= 0 && ix < p.Ws;
+      const int cx = min(max(ix, 0), p.Ws - 1);
+      colo[a][dd] = (p.xinv ? __ldg(p.xinv + cx) : cx) * ldz + kx * p.Cout;
+    }
+  act_t raw[2][2][2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) raw[a][b][dy][dx] = zr[rowo[a][dy] + colo[b][dx]];
   float acc = 0.f;
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const int yy = Y[a], xx = X[b];
       float v = 0.f;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int ky = ((yy + 1) & 1) + 2 * dy, kx = ((xx + 1) & 1) + 2 * dx;
-          const int iy = (yy + 1 - ky) >> 1, ix = (xx + 1 - kx) >> 1;
-          if (iy >= 0 && iy < p.Hs && ix >= 0 && ix < p.Ws)
-            v += act2f(zr[((size_t)iy * p.Ws + ix) * ldz + (ky * 4 + kx) * p.Cout]);
-        }
+        for (int dx = 0; dx < 2; ++dx)
+          if (rok[a][dy] && cok[b][dx]) v += act2f(raw[a][b][dy][dx]);
       acc = fmaf(wy[a] * wx[b], v, acc);
     }
   p.y[(((size_t)r * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = acc + __ldg(p.bias + co);
@@ -960,7 +987,7 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
     }
     if (p.bilinear || p.Hi != p.Ho || p.Wi != p.Wo) { set_error("pack x-im2col: no resize"); return -1; }
     ProfScope prof(s, KC_PACK);
-    pack_xim2col_kernel<<<cdiv((long long)p.rows * p.Ho * p.Wo, 256), 256, 0, s>>>(q, ch);
+    pack_xim2col_kernel<<<row_grid(p.rows, (long long)p.Ho * p.Wo), 256, 0, s>>>(q, ch);
     DYF_LAUNCH_OK("pack_xim2col_kernel");
     return 0;
   }
@@ -968,7 +995,6 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
     int ctot = 0;
     for (int i = 0; i < p.nsrc; ++i) ctot += p.C[i];
     if (ctot > 15 || p.ones_channel != ctot || p.noise_src >= 0) { set_error("pack s2d: needs <= 15 input channels"); return -1; }
-    const long long total = (long long)p.rows * p.Ho * p.Wo * 4;
     S2dChannels ch{};
     const size_t plane = (size_t)p.Hi * p.Wi;
     for (int i = 0; i < p.nsrc; ++i)
@@ -977,14 +1003,21 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
         ch.row_stride[ch.n] = (int)(p.C[i] * plane);
       }
     ProfScope prof(s, KC_PACK);
-    pack_s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(p, ch);
+    const unsigned grid = row_grid(p.rows, (long long)p.Ho * p.Wo * 4);
+    switch (ch.n) {
+#define DYF_S2D_CASE(N) case N: pack_s2d_kernel<N><<<grid, 256, 0, s>>>(p, ch); break;
+      DYF_S2D_CASE(1) DYF_S2D_CASE(2) DYF_S2D_CASE(3) DYF_S2D_CASE(4) DYF_S2D_CASE(5) DYF_S2D_CASE(6) DYF_S2D_CASE(7)
+      DYF_S2D_CASE(8) DYF_S2D_CASE(9) DYF_S2D_CASE(10) DYF_S2D_CASE(11) DYF_S2D_CASE(12) DYF_S2D_CASE(13) DYF_S2D_CASE(14)
+      DYF_S2D_CASE(15)
+#undef DYF_S2D_CASE
+      default: set_error("pack s2d: needs 1..15 input channels"); return -1;
+    }
     DYF_LAUNCH_OK("pack_s2d_kernel");
     return 0;
   }
   if (p.Cpad % 8 != 0) { set_error("pack: Cpad must be a multiple of 8"); return -1; }
-  const long long total = (long long)p.rows * p.Ho * p.Wo;
   ProfScope prof(s, KC_PACK);
-  pack_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  pack_kernel<<<row_grid(p.rows, (long long)p.Ho * p.Wo), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("pack_kernel");
   return 0;
 }
@@ -1003,13 +1036,13 @@ int launch_upsample(const UpsampleParams& p, cudaStream_t s) {
   if (p.scale == 2 && p.bilinear) {
     const long long quads = (long long)p.rows * p.H * p.W * ((p.C[0] + p.C[1]) >> 3);
     ProfScope prof(s, KC_UPSAMPLE, 0.0, 2.0 * 5.0 * (double)quads * 8);
-    upsample2x_quad_kernel<<<cdiv(quads, 256), 256, 0, s>>>(p);
+    upsample2x_quad_kernel<<<row_grid(p.rows, (long long)p.H * p.W * ((p.C[0] + p.C[1]) >> 3)), 256, 0, s>>>(p);
     DYF_LAUNCH_OK("upsample2x_quad_kernel");
     return 0;
   }
   const long long total = (long long)p.rows * p.H * p.scale * p.W * p.scale * ((p.C[0] + p.C[1]) >> 3);
   ProfScope prof(s, KC_UPSAMPLE, 0.0, 2.0 * 1.25 * (double)total * 8);
-  upsample_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  upsample_kernel<<<row_grid(p.rows, (long long)p.H * p.scale * p.W * p.scale * ((p.C[0] + p.C[1]) >> 3)), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("upsample_kernel");
   return 0;
 }
@@ -1078,9 +1111,8 @@ int launch_readout(const ReadoutParams& p, cudaStream_t s) {
 }
 
 int launch_readout_gather(const ReadoutGatherParams& p, cudaStream_t s) {
-  const long long total = (long long)p.rows * p.Ho * p.Wo * p.Cout;
   ProfScope prof(s, KC_READOUT);
-  readout_gather_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
+  readout_gather_kernel<<<row_grid(p.rows, (long long)p.Ho * p.Wo * p.Cout), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("readout_gather_kernel");
   return 0;
 }

@@ -107,6 +107,21 @@ struct Philox {
   }
 };
 
+// Division by a run-time constant as multiply-high + shift (n, d < 2^31; Granlund-Montgomery round-up multiplier).  The
+// work-item decoding of the persistent kernels runs in every warp for every item: a 32-bit division by a kernel parameter is
+// ~35 instructions, and on short items (single-chunk 1x1 / stem layers) those divisions were most of the issue slots.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  FastDiv() = default;
+  explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
+    while ((1ull << shr) < div) ++shr;
+    mul = (uint32_t)(((((1ull << shr) - div) << 32) / div) + 1);
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, mul) + n) >> shr; }
+#endif
+};
+
 // Dropout of a run of 8 consecutive elements (first element index a multiple of 8).  keep-bit j uses 16 random bits;
 // P(keep) = 1 - thresh/65536.  The mask is a pure function of (seed, logical call, site, GLOBAL row, element inside the
 // row): a batch row b of a launch sequence that carries several logical calls of `group_rows` rows each is row

@@ -10,6 +10,8 @@ struct ConvParams {
   const act_t* in;   // [rows, Hi, Wi, Cin]      (Cin % 8 == 0)
   const act_t* in2;  // optional second source [rows, Hi, Wi, Cin - Cin0]: the input is the channel concat
   int Cin0;                  //   [in | in2] without a concat buffer (tcgen05 TMA path only); 0 = single source
+  const int* in_xmap;        // optional (1x1, tcgen05 gather path only): output column x reads input column in_xmap[x], Wo
+                             //   entries -- a 1x1 conv evaluated on a subset of the input columns (NS readout)
   const act_t* w_umma;  // weights re-packed as UMMA stage tiles (conv_umma.cu) or nullptr
   const act_t* w;    // [Cout, Kpad]  k = (ky*KW + kx)*Cin + c, zero padded to Kpad (multiple of 32)
   void* out;                 // bf16 [M, out_ld] (+out_coff) or fp32 when out_fp32

@@ -49,7 +49,7 @@ struct __align__(8) FBarriers {
 // Launch-side geometry of one layer, and the whole network call: up to FLAT_MAX_LAYERS layers run inside ONE persistent
 // kernel (cooperative launch), separated by grid-wide barriers -- a layer reads, through TMA, raster positions that other
 // CTAs' epilogues wrote.  All pipelines (patch ring, weight ring, TMEM ping-pong) keep their state across the layers.
-struct FlatLayerCfg { int box_rows, nbox, num_work, items_per_call; };
+struct FlatLayerCfg { int box_rows, nbox, num_work, items_per_call; FastDiv d_items, d_PI, d_S; };  // (d_*: divisions by items_per_call / PI_in / S_in)
 struct FlatNetParams {
   int nlayers, BS, a_stage;   // weight-ring depth, patch stage stride (the largest layer's)
   FlatConvParams L[FLAT_MAX_LAYERS];
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
   const FlatConvParams& p = P.L[layer];
   const int box_rows = P.G[layer].box_rows, nbox = P.G[layer].nbox, num_work = P.G[layer].num_work,
             items_per_call = P.G[layer].items_per_call;
+  const FastDiv d_items = P.G[layer].d_items, d_PI = P.G[layer].d_PI, d_S = P.G[layer].d_S;
   const int nchunks = p.Cin / 64;
   if (warp < EPI_WARPS) {
     // =============================== epilogue: TMEM -> tables / activation / dropout / residual -> next raster ==========
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
     int tab_key = -1, tab_buf = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++e_it) {
       const int it = e_it;
-      const int call = w / items_per_call, t0 = (w - call * items_per_call) * ITEM_POS;
+      const int call = (int)d_items.div((uint32_t)w), t0 = (w - call * items_per_call) * ITEM_POS;
       const int acc = it & 1;
       if (call != tab_key) {  // epilogue tables of this logical call -> shared memory (other buffer: one barrier suffices)
         tab_key = call;
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
       for (int u = 0; u < 2; ++u) {
         if (u >= nu) { valid[u] = false; continue; }
         lp[u] = t0 + u_tile[u] * 128 + quarter * 32 + lane;
-        img[u] = lp[u] / p.PI_in;
+        img[u] = (int)d_PI.div((uint32_t)lp[u]);
         const int rem = lp[u] - img[u] * p.PI_in;
-        yy[u] = rem / p.S_in; xx[u] = rem - yy[u] * p.S_in;
+        yy[u] = (int)d_S.div((uint32_t)rem); xx[u] = rem - yy[u] * p.S_in;
         valid[u] = img[u] < p.G && yy[u] < p.H && xx[u] < p.W;
         if (p.res && valid[u]) {  // residual = this layer's input at the same pixel = the same raster position
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + ((size_t)call * p.PC_in + lp[u]) * BN + u_col[u]);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
     if (lane == 0) {
       const CUtensorMap* tm = layer == 0 ? &tm0 : layer == 1 ? &tm1 : layer == 2 ? &tm2 : &tm3;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int call = w / items_per_call, t0 = (w - call * items_per_call) * ITEM_POS;
+        const int call = (int)d_items.div((uint32_t)w), t0 = (w - call * items_per_call) * ITEM_POS;
         const int g0 = call * p.PC_in + t0 - p.halo;  // first patch position (negative before the raster: zero fill)
         for (int c = 0; c < nchunks; ++c, ++a_ca) {
           const int st = a_ca % AS;
@@ -320,12 +321,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
 // One thread per SOURCE pixel: it builds the pixel's slot vector once (one coalesced load per channel plane) and stores it
 // into the <= k positions that see it through one of their horizontal taps.
 __global__ void __launch_bounds__(256) pack_flat_kernel(const FlatPackParams p) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, y, xs)
-  if (idx >= (long long)p.rows * p.H * p.W) return;
-  const int xs = (int)(idx % p.W);
-  const long long t = idx / p.W;
-  const int y = (int)(t % p.H), r = (int)(t / p.H);
-  const int call = r / p.G, img = r - call * p.G, rs = r % p.src_rows;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // (row, y, xs): 32-bit (checked by the launcher)
+  if (idx >= (unsigned)p.rows * p.H * p.W) return;
+  const unsigned t = idx / (unsigned)p.W;
+  const int xs = (int)(idx - t * p.W);
+  const int r = (int)(t / (unsigned)p.H), y = (int)(t - (unsigned)r * p.H);
+  const int call = (int)((unsigned)r / (unsigned)p.G), img = r - call * p.G, rs = (int)((unsigned)r % (unsigned)p.src_rows);
   const int pix = y * p.W + xs;
   float v[16];
 #pragma unroll
@@ -412,6 +413,7 @@ bool conv_flat_shape_ok(int H, int W, int k, int Cout) {
 int launch_pack_flat(const FlatPackParams& p, cudaStream_t s) {
   ProfScope prof(s, KC_PACK);
   const long long total = (long long)p.rows * p.H * p.W;
+  if (total > 0x7fffffffLL) { set_error("pack_flat: too many source pixels"); return -1; }
   pack_flat_kernel<<<cdiv(total, 256), 256, 0, s>>>(p);
   DYF_LAUNCH_OK("pack_flat_kernel");
   return 0;
@@ -457,6 +459,7 @@ int launch_conv_flat_net(const FlatConvParams* layers, int nlayers, cudaStream_t
     P.G[l].box_rows = box_rows; P.G[l].nbox = nbox;
     P.G[l].items_per_call = p.PC_in / ITEM_POS;
     P.G[l].num_work = p.calls * P.G[l].items_per_call;
+    P.G[l].d_items = FastDiv((uint32_t)P.G[l].items_per_call); P.G[l].d_PI = FastDiv((uint32_t)p.PI_in); P.G[l].d_S = FastDiv((uint32_t)p.S_in);
     max_work = std::max(max_work, P.G[l].num_work);
     const long long positions = (long long)p.calls * p.PC_in;
     const Key key{p.in, positions, p.Cin, box_rows};

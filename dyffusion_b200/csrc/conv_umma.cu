@@ -63,9 +63,9 @@ template <int T> struct Geo<S1K3, T> {
   __device__ static int in_y(int oy0, int pr) { return oy0 - 1 + pr; }
   __device__ static int in_x(int ox0, int pc) { return ox0 - 1 + pc; }
 };
-template <int T> struct Geo<S1K1, T> {  // 1x1 convolution = plain GEMM over the 16 x 8 pixel tile (no halo, one "tap")
+template <int T> struct Geo<S1K1, T> {  // 1x1 convolution = plain GEMM over the 16 x 8T pixel tile (no halo, one "tap")
   static constexpr int CH = 64, PLANES = 8, CPL = 8;
-  static constexpr int PH = TILE_H, PW = TILE_W;
+  static constexpr int PH = TILE_H, PW = TILE_W * T;
   static constexpr int PIX = PH * PW, SLOTS = PIX;
   static constexpr int TAPS = 1, KW = 1, GT = 1, HALO = 0;
   static constexpr int SBO = PW * 16;
@@ -112,6 +112,8 @@ template <int MODE, int T = 1> struct Sizes {
   static constexpr int KSTEPS = G::CH / 16;
 };
 
+struct WorkDiv { FastDiv n_tiles, per_row, tiles_x, tab, grp; };  // divisors of the work-item decoding, table row, RNG row group
+
 template <int AS, int BS>
 struct __align__(8) Barriers {
   uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
@@ -133,14 +135,15 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
                                                               const __grid_constant__ CUtensorMap tmap,
                                                               const __grid_constant__ CUtensorMap tmap2,
                                                               const __grid_constant__ CUtensorMap tmap3,
-                                                              const __grid_constant__ CUtensorMap tmap4, int nch_split) {
+                                                              const __grid_constant__ CUtensorMap tmap4, int nch_split,
+                                                              const WorkDiv wd) {
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
   constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
   constexpr bool S2TMA = TMA && MODE == S2K4;
   constexpr int CHK = S2TMA ? 64 : G::CH;   // channels per chunk (the stride-2 TMA path uses 64: 128-byte pixel rows)
   constexpr int PLANE = S::PLANE, KSTEPS = CHK / 16;
-  static_assert(TMA || T == 1 || MODE == S2K4, "multi-tile gathered patches: stride-2 mode only");
+  static_assert(TMA || T == 1 || MODE == S2K4 || MODE == S1K1, "multi-tile gathered patches: stride-2 and 1x1 modes only");
   static_assert(G::TAPS % GT == 0, "weight stages must tile the filter");
   constexpr int PWT = TILE_W * T + G::HALO;  // patch width of the super-tile (TMA mode)
   constexpr int PIXT = G::PH * PWT;
@@ -192,11 +195,11 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
 
   // work item -> (n_tile, batch row, tile origin)
   auto decode = [&](int w, int& n_tile, int& row, int& oy0, int& ox0) {
-    n_tile = w % n_tiles;
-    int t = w / n_tiles;
-    row = t / tiles_per_row;
+    int t = (int)wd.n_tiles.div((uint32_t)w);
+    n_tile = w - t * n_tiles;
+    row = (int)wd.per_row.div((uint32_t)t);
     t -= row * tiles_per_row;
-    const int ty = t / tiles_x;
+    const int ty = (int)wd.tiles_x.div((uint32_t)t);
     oy0 = ty * TILE_H;
     ox0 = (t - ty * tiles_x) * (TILE_W * T);
   };
@@ -213,20 +216,22 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       int n_tile, row, oy0, ox0;
       decode(w, n_tile, row, oy0, ox0);
       const int acc = it & 1;
-      const DropRow dr = drop_row(p.drop, row, (uint64_t)p.Ho * p.Wo * p.Cout);
+      const uint32_t gj = wd.grp.div((uint32_t)row), gr = (uint32_t)row - gj * p.drop.group_rows;  // = drop_row()
+      const DropRow dr{p.drop.stream_lo + gj, (uint64_t)(gr + p.drop.row_off) * ((uint64_t)p.Ho * p.Wo * p.Cout)};
       const int quarter = warp & 3;          // TMEM lanes 32*quarter.. are the ones this warp may read
       const int m_local = quarter * 32 + lane;  // accumulator row = TMEM lane
       const int oy = oy0 + (m_local >> 3);
       // epilogue tables of (table row, n-tile) staged in shared memory; re-staged only when the key changes (contiguous
       // work ranges: once per image), into the other buffer so that one barrier per change suffices
-      const int tkey = (row / p.tab_div) * n_tiles + n_tile;
+      const int trow = (int)wd.tab.div((uint32_t)row);  // table row (rows of one logical call share it)
+      const int tkey = trow * n_tiles + n_tile;
       if (tkey != tab_key) {
         tab_key = tkey;
         tab_buf ^= 1;
         float* const dst = sTab + tab_buf * 2 * BN;
         if (tid < BN) {
           const int col = n_tile * BN + tid;
-          const size_t off = (size_t)(row / p.tab_div) * p.Cout + col;
+          const size_t off = (size_t)trow * p.Cout + col;
           dst[tid] = col < p.Cout ? __ldg(p.tabA + off) : 0.f;
           dst[BN + tid] = col < p.Cout ? __ldg(p.tabB + off) : 0.f;
         }
@@ -262,7 +267,8 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
           y[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a.z, b.z);
           y[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a.w, b.w);
         }
-        if (act <= ACT_LEAKY) {  // identity / ReLU / LeakyReLU(0.2) = max(y, slope * y) with slope 1 / 0 / 0.2
+        if (act == ACT_NONE) {
+        } else if (act <= ACT_LEAKY) {  // ReLU / LeakyReLU(0.2) = max(y, slope * y) with slope 0 / 0.2
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], slope * y[j]);
         } else if (act == ACT_SILU) {
@@ -361,8 +367,11 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
         int so = -1, dof = -1;
         if (pix < G::PIX) {
           const int pr = pix / G::PW, pc = pix - pr * G::PW;
-          const int iy = G::in_y(oy0, pr), ix = G::in_x(ox0, pc);
-          if ((unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)p.Wi) so = (iy * p.Wi + ix) * p.Cin;
+          const int iy = G::in_y(oy0, pr);
+          int ix = G::in_x(ox0, pc);
+          bool ok = (unsigned)iy < (unsigned)p.Hi && (unsigned)ix < (unsigned)(p.in_xmap ? p.Wo : p.Wi);
+          if (ok && p.in_xmap) ix = __ldg(p.in_xmap + ix);  // column subset: virtual output column -> input column
+          if (ok) so = (iy * p.Wi + ix) * p.Cin;
           dof = G::plane_of(g8, pc) * PLANE + G::slot(pr, pc) * 16;
         }
         src_off[it] = so;
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
       for (int w0 = blockIdx.x * cw; w0 < num_work && !(b_resident && loaded); w0 += gridDim.x * cw)
       for (int w = w0; w < min(w0 + cw, num_work) && !(b_resident && loaded); ++w) {
         loaded = true;
-        const int n_tile = w % n_tiles;
+        const int n_tile = w - (int)wd.n_tiles.div((uint32_t)w) * n_tiles;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wblob) + (size_t)n_tile * per_tile * B_STAGE;
         for (int i = 0; i < per_tile; ++i) {
           int j = i;
@@ -553,6 +562,7 @@ template <> struct Stages<S1K1, 64, true, 1> { static constexpr int T = 1, GT = 
 template <> struct Stages<S1K1, 128, true, 1> { static constexpr int T = 1, GT = 1, A = 6, B = 6; };
 template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
+template <> struct Stages<S1K1, 64, false, 2> { static constexpr int T = 2, GT = 1, A = 5, B = 1; };  // column-subset readout: resident filter, deep gather ring
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
 template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 1, A = 4, B = 8; };    // 148 KB (4 view stages) + 64 KB weights
@@ -605,11 +615,13 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   const long long work = (long long)tiles_x * tiles_y * p.rows * n_tiles;
   if (work > 0x7fffffffLL) { set_error("conv_umma: too many tiles"); return -1; }
   const int grid = (int)(work < num_sms ? work : num_sms);
+  const WorkDiv wd{FastDiv((uint32_t)n_tiles), FastDiv((uint32_t)(tiles_x * tiles_y)), FastDiv((uint32_t)tiles_x),
+                   FastDiv((uint32_t)(p.tab_div > 0 ? p.tab_div : 1)), FastDiv(p.drop.group_rows ? p.drop.group_rows : 1u)};
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
-  const double bytes = 2.0 * ((double)p.rows * p.Hi * p.Wi * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
+  const double bytes = 2.0 * ((double)p.rows * p.Hi * (p.in_xmap ? p.Wo : p.Wi) * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
   conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
-                                                                                (int)work, tmap, tmap2, tmap3, tmap4, nch_split);
+                                                                                (int)work, tmap, tmap2, tmap3, tmap4, nch_split, wd);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
 }
@@ -650,6 +662,7 @@ bool conv_umma_eligible(const ConvParams& p) {
     const int mode = mode_of(p.KH, p.stride, p.pad);
     if ((mode != S1K3 && mode != S1K1) || p.Cin0 <= 0 || p.Cin0 % 64 || (p.Cin - p.Cin0) % 64) return false;
   }
+  if (p.in_xmap && (p.in2 || mode_of(p.KH, p.stride, p.pad, p.KW) != S1K1)) return false;
   if (mode_of(p.KH, p.stride, p.pad, p.KW) == S1K7V)
     return p.w_umma != nullptr && !p.in2 && p.Cin == 64 && (p.Cout == 64 || p.Cout % 128 == 0) && p.out_fp32 == 0 &&
            ((p.out_ld | p.out_coff) & 7) == 0 && (!p.res || (p.res_ld & 7) == 0);
@@ -713,10 +726,11 @@ int launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
     return n64 ? launch_t<64, S1K3, false>(p, stream) : launch_t<128, S1K3, false>(p, stream);
   }
   if (mode == S1K1) {
-    if (want_tma) {
+    if (want_tma && !p.in_xmap) {  // (a column subset is not a tensor-map box: cp.async gather)
       const int rc = n64 ? launch_t<64, S1K1, true>(p, stream) : launch_t<128, S1K1, true>(p, stream);
       if (rc != 0 || p.in2) return rc;
     }
+    if (p.in_xmap && n64 && p.Cin == 64) return launch_t<64, S1K1, false, 2>(p, stream);
     return n64 ? launch_t<64, S1K1, false>(p, stream) : launch_t<128, S1K1, false>(p, stream);
   }
   // The stride-2 weight tiles were packed (finalize) for 64-channel chunks iff Cin % 64 == 0 and the TMA path is on: those

@@ -29,6 +29,7 @@ struct ConvLayer {
   bool standardize = false;                   // WeightStandardizedConv2d
   int K = 0, Kpad = 0;
   size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
+  int xmap_cols = 0;                            // > 0: 1x1 conv over a column subset of its input (Net::ro_xmap), output width
   int convt_z = 0;                              // weight = ConvTranspose2d [Cin, Cout/16, 4, 4] re-laid out as a 1x1 conv
   int comp_s2d = 0;                             // composite expressed as 3x3/s1 over the space-to-depth packed input
   int flops_cin = 0;                            // channels to count per tap in FLOP accounting (0 = Cin)
@@ -93,6 +94,10 @@ struct Net {
   std::vector<TimeLayer> time_layers;
   int t_w1 = -1, t_b1 = -1, t_w2 = -1, t_b2 = -1;
   int ro_w = -1, ro_b = -1;  // readout params
+  // NS readout on the source columns the final resize samples: virtual column -> source column (ro_xmap) and back (ro_xinv)
+  std::vector<int> ro_xmap, ro_xinv;
+  int* ro_tab_dev = nullptr;  // [ro_xmap | ro_xinv] on the device (finalize)
+  int ro_src_w = 0;
   int time_dim = 0;
   long long tab_floats_per_row = 0;    // sum of C over time_layers
   long long stats_floats_per_row = 0;

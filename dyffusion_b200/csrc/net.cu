@@ -20,6 +20,7 @@ Net::~Net() {
   if (wq_umma) cudaFree(wq_umma);
   if (d_time_layers) cudaFree(d_time_layers);
   if (flat_mem) cudaFree(flat_mem);
+  if (ro_tab_dev) cudaFree(ro_tab_dev);
   clear_tab_cache();
 }
 
@@ -295,8 +296,42 @@ int Net::build_unet_simple() {
     z.K = dim; z.Kpad = round_up(dim, 32);
     z.wq_off = wq_elems; wq_elems += (size_t)z.Cout * z.Kpad;
     if (conv_umma_shape_ok(z.Cpad, z.Cout, 1, 1, 0)) { z.wu_off = (long long)wu_elems; wu_elems += (size_t)umma_padded_cout(z.Cout) * z.Cin; }
+    // Source columns the outer resize reads (two bilinear corners x two transposed-conv taps per output column): for
+    // 512 -> 42 that is 126 of 256 columns, so the 1x1 conv is evaluated on those only (cp.async gather through a column
+    // table) and z is stored compactly.  Corner indices are taken for src -+ eps: a superset of what the device's float
+    // arithmetic in bilinear_coord can produce.
+    ro_src_w = bufs[x].W;
+    int zw = bufs[x].W;
+    if (z.wu_off >= 0 && !getenv("DYF_DISABLE_READOUT_COLS") && !getenv("DYF_DISABLE_UMMA")) {
+      const int Ws = bufs[x].W, W2 = 2 * Ws;
+      std::vector<char> need(Ws, 0);
+      const double scale = (double)W2 / d.width;
+      for (int ox = 0; ox < d.width; ++ox)
+        for (int e = -1; e <= 1; e += 2) {
+          double src = scale * (ox + 0.5) - 0.5 + e * 1e-3;
+          if (src < 0) src = 0;
+          int x0 = (int)src;
+          if (x0 > W2 - 1) x0 = W2 - 1;
+          const int xs[2] = {x0, x0 + (x0 < W2 - 1 ? 1 : 0)};
+          for (int xx : xs)
+            for (int dx = 0; dx < 2; ++dx) {
+              const int kx = ((xx + 1) & 1) + 2 * dx, ix = (xx + 1 - kx) >> 1;
+              if (ix >= 0 && ix < Ws) need[ix] = 1;
+            }
+        }
+      std::vector<int> cols;
+      for (int i = 0; i < Ws; ++i) if (need[i]) cols.push_back(i);
+      const int wv = round_up((int)cols.size(), 8);
+      if (!cols.empty() && wv * 4 <= Ws * 3) {
+        ro_xinv.assign(Ws, 0);
+        for (size_t i = 0; i < cols.size(); ++i) ro_xinv[cols[i]] = (int)i;
+        ro_xmap = cols;
+        ro_xmap.resize(wv, cols.back());  // padding columns re-read the last one (never gathered)
+        z.xmap_cols = zw = wv;
+      }
+    }
     convs.push_back(z);
-    int zb = add_buf(bufs[x].H, bufs[x].W, 16 * d.out_channels);
+    int zb = add_buf(bufs[x].H, zw, 16 * d.out_channels);
     Op c{}; c.type = OP_CONV; c.in0 = x; c.out = zb; c.layer = (int)convs.size() - 1; c.act = ACT_NONE;
     ops.push_back(c);
     Op g{}; g.type = OP_READOUT_GATHER; g.in0 = zb;
@@ -613,6 +648,12 @@ int Net::finalize(cudaStream_t s) {
     if (!p.is_set && !p.ignored) { set_error("missing state-dict key: " + p.key); return DYF_ERR_STATE; }
   if (!wq) DYF_CUDA_OK(cudaMalloc(&wq, wq_elems * sizeof(act_t)));
   if (!wq_umma && wu_elems) DYF_CUDA_OK(cudaMalloc(&wq_umma, wu_elems * sizeof(act_t)));
+  if (!ro_xmap.empty() && !ro_tab_dev) {  // readout column tables: [virtual -> source | source -> virtual]
+    std::vector<int> tab(ro_xmap);
+    tab.insert(tab.end(), ro_xinv.begin(), ro_xinv.end());
+    DYF_CUDA_OK(cudaMalloc(&ro_tab_dev, tab.size() * sizeof(int)));
+    DYF_CUDA_OK(cudaMemcpy(ro_tab_dev, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   for (auto& c : convs) {
     if (c.up_off[0] >= 0) {  // fused upsample + conv: composite weight variants (conv_up.cu)
       float* scratch = nullptr;
@@ -908,6 +949,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         p.Ho = (bi.H + 2 * c.pad - c.KH) / c.stride + 1;
         p.Wo = (bi.W + 2 * c.pad - c.KW) / c.stride + 1;
         if (c.stem_xim2col) p.Wo = bi.W;  // vertical taps only: no horizontal padding
+        if (c.xmap_cols) { p.in_xmap = ro_tab_dev; p.Wo = c.xmap_cols; }  // 1x1 over a column subset (NS readout)
         p.Cout = c.Cout; p.KH = c.KH; p.KW = c.KW; p.stride = c.stride; p.pad = c.pad; p.K = c.K; p.Kpad = c.Kpad;
         p.tabA = tabA + (size_t)time_layers[c.table].tab_off * tab_rows;
         p.tabB = tabB + (size_t)time_layers[c.table].tab_off * tab_rows;
@@ -923,6 +965,7 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
         }
         if (p.Cin != c.Cpad) { set_error("internal: conv input channel mismatch"); return DYF_ERR_STATE; }
         rc = launch_conv_umma(p, s);
+        if (rc == 0 && c.xmap_cols) { set_error("internal: the column-subset readout needs the tcgen05 gather path"); return DYF_ERR_STATE; }
         if (rc == 0 && c.stem_xim2col) { set_error("internal: the x-im2col stem needs the tcgen05 TMA path"); return DYF_ERR_STATE; }
         if (rc == 0 && p.in2) { set_error("internal: two-source conv needs the tcgen05 TMA path"); return DYF_ERR_STATE; }
         if (rc == 0) rc = launch_conv_mma(p, s);
@@ -973,7 +1016,8 @@ int Net::forward(int rows, const float* const* srcs, const int* src_ch, int nsrc
       case OP_READOUT_GATHER: {
         ReadoutGatherParams p{};
         p.z = bp[o.in0]; p.bias = packed + params[ro_b].off; p.y = y;
-        p.rows = rows; p.Hs = bufs[o.in0].H; p.Ws = bufs[o.in0].W; p.Cout = d.out_channels; p.Ho = d.height; p.Wo = d.width;
+        p.rows = rows; p.Hs = bufs[o.in0].H; p.Ws = ro_src_w; p.Wz = bufs[o.in0].W; p.Cout = d.out_channels; p.Ho = d.height; p.Wo = d.width;
+        if (!ro_xmap.empty()) p.xinv = ro_tab_dev + ro_xmap.size();
         rc = launch_readout_gather(p, s);
         break;
       }
