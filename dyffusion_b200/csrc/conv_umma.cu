@@ -39,8 +39,10 @@ namespace {
 constexpr int TILE_H = 16, TILE_W = 8;  // output pixels per CTA tile (M = 128)
 constexpr int EPI_WARPS = 8;    // two warps per TMEM lane quarter, each draining half of the accumulator columns
 // epilogue + patch-producer warps (1 issuing thread with TMA, 8 gathering warps with cp.async) + MMA warp + weight warp
-__host__ __device__ constexpr int prod_warps(bool tma) { return tma ? 1 : 8; }
-__host__ __device__ constexpr int cta_threads(bool tma) { return (EPI_WARPS + prod_warps(tma) + 2) * 32; }
+// (the 1x1 gather kernel -- the NS readout over a column subset -- runs 4 gather warps: 448 threads leave its epilogue 144
+// registers per thread; with 8 gather warps the 96-register cap spilled the epilogue's column block to local memory)
+__host__ __device__ constexpr int prod_warps(bool tma, int mode) { return tma ? 1 : mode == 2 /* S1K1 */ ? 4 : 8; }
+__host__ __device__ constexpr int cta_threads(bool tma, int mode) { return (EPI_WARPS + prod_warps(tma, mode) + 2) * 32; }
 
 enum Mode { S1K3 = 0, S2K4 = 1, S1K1 = 2, S2K2 = 3, S1K7V = 4 };  // S2K2 (2x2 / stride 2 / pad 0) runs on the S1K1 kernel, see launch_s2k2
 // S1K7V: 7 VERTICAL taps (7x1 filter, pad 3 vertically, none horizontally) over 64 channels -- the SST stem (7x7, C_in <= 8)
@@ -130,7 +132,7 @@ struct __align__(8) Barriers {
 // is released, so a weight byte pulled from L2 feeds T x 128 GEMM rows; the patch of the 16 x 8T super-tile is one TMA
 // box and each tile's taps are start-address shifts inside it.  GT = filter taps per weight stage.
 template <int BN, int MODE, int AS, int BS, bool TMA, int T, int GT>
-__global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const ConvParams p, const act_t* __restrict__ wblob,
+__global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(const ConvParams p, const act_t* __restrict__ wblob,
                                                               int tiles_x, int tiles_y, int n_tiles, int num_work,
                                                               const __grid_constant__ CUtensorMap tmap,
                                                               const __grid_constant__ CUtensorMap tmap2,
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(cta_threads(TMA), 1) conv_umma_kernel(const Co
                                                               const WorkDiv wd) {
   using G = Geo<MODE, TMA ? 1 : T>;
   using S = Sizes<MODE, TMA ? 1 : T>;
-  constexpr int PROD_WARPS = prod_warps(TMA), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
+  constexpr int PROD_WARPS = prod_warps(TMA, MODE), PROD_THREADS = PROD_WARPS * 32, MMA_WARP = EPI_WARPS + PROD_WARPS;
   constexpr bool S2TMA = TMA && MODE == S2K4;
   constexpr int CHK = S2TMA ? 64 : G::CH;   // channels per chunk (the stride-2 TMA path uses 64: 128-byte pixel rows)
   constexpr int PLANE = S::PLANE, KSTEPS = CHK / 16;
@@ -562,7 +564,7 @@ template <> struct Stages<S1K1, 64, true, 1> { static constexpr int T = 1, GT = 
 template <> struct Stages<S1K1, 128, true, 1> { static constexpr int T = 1, GT = 1, A = 6, B = 6; };
 template <> struct Stages<S1K1, 64, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
 template <> struct Stages<S1K1, 128, false> { static constexpr int T = 1, GT = 1, A = 6, B = 4; };
-template <> struct Stages<S1K1, 64, false, 2> { static constexpr int T = 2, GT = 1, A = 5, B = 1; };  // column-subset readout: resident filter, deep gather ring
+template <> struct Stages<S1K1, 64, false, 2> { static constexpr int T = 1, GT = 1, A = 10, B = 1; };  // column-subset readout: resident filter, deep gather ring
 template <> struct Stages<S2K4, 64, false> { static constexpr int T = 2, GT = 2, A = 2, B = 8; };   // 145 KB patches +  64 KB weights
 template <> struct Stages<S2K4, 128, false> { static constexpr int T = 2, GT = 1, A = 2, B = 9; };  // 145 KB patches +  72 KB weights
 template <> struct Stages<S2K4, 64, true> { static constexpr int T = 2, GT = 1, A = 4, B = 8; };    // 148 KB (4 view stages) + 64 KB weights
@@ -620,7 +622,7 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * (p.in_xmap ? p.Wo : p.Wi) * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
+  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA, MODE), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
                                                                                 (int)work, tmap, tmap2, tmap3, tmap4, nch_split, wd);
   DYF_LAUNCH_OK("conv_umma_kernel");
   return 1;
