@@ -601,16 +601,17 @@ __global__ void __launch_bounds__(GNF_THREADS, GNF_MINB) groupnorm_fused_kernel(
       unpack8(u[k], f);
       {
         const float4 a0 = sA4[0], a1 = sA4[1], b0 = sB4[0], b1 = sB4[1];
-        f[0] = apply_act(fmaf(f[0], a0.x, b0.x), p.act); f[1] = apply_act(fmaf(f[1], a0.y, b0.y), p.act);
-        f[2] = apply_act(fmaf(f[2], a0.z, b0.z), p.act); f[3] = apply_act(fmaf(f[3], a0.w, b0.w), p.act);
-        f[4] = apply_act(fmaf(f[4], a1.x, b1.x), p.act); f[5] = apply_act(fmaf(f[5], a1.y, b1.y), p.act);
-        f[6] = apply_act(fmaf(f[6], a1.z, b1.z), p.act); f[7] = apply_act(fmaf(f[7], a1.w, b1.w), p.act);
+        f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+        f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
       }
-      if (p.drop.thresh) {
-        const uint32_t keep = drop_keep_bits8(p.drop, dr, (uint64_t)q * p.C + (ch << 3));
+      if (p.act == ACT_SILU) {  // (the activation switch stays outside the element loop: the pass is issue-bound)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = ((keep >> j) & 1u) ? f[j] * p.drop.scale : 0.f;
+        for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-f[j]));
+      } else if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
       }
+      if (p.drop.thresh) drop_apply8(p.drop, dr, (uint64_t)q * p.C + (ch << 3), f);
       if (res) {
         float g[8];
         unpack8(rr[k], g);

@@ -76,12 +76,30 @@ __device__ __forceinline__ float erf_fast(float z) {
   return copysignf(1.f - poly * __expf(-az * az), z);
 }
 
+// nn.GELU() (erf form) as v * Phi(v) with the normal CDF's tail written as a power of two: 0.5 erfc(a / sqrt 2) = 2^P(a),
+// a = min(|v|, 6), P a degree-7 polynomial (weighted Chebyshev fit of log2 of the tail, evaluated in fp32 Horner form):
+// |GELU error| <= 7.4e-8, |Phi error| <= 2.0e-7 over the whole line (tests/micro/gelu_fit.py) -- 7 FMAs + one exp2 instead of
+// the 20 instructions of the erf route; the GELU epilogues of the spring-mesh layers are issue-bound.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float a = fminf(fabsf(v), 6.f);
+  float p = 4.206899575365242e-06f;
+  p = fmaf(p, a, -1.211548806168139e-05f);
+  p = fmaf(p, a, -0.0005781833897344768f);
+  p = fmaf(p, a, 0.007674761116504669f);
+  p = fmaf(p, a, -0.05295220762491226f);
+  p = fmaf(p, a, -0.4590412676334381f);
+  p = fmaf(p, a, -1.1511286497116089f);
+  p = fmaf(p, a, -0.999999463558197f);
+  const float e = exp2f(p);           // Phi(-|v|)   (-use_fast_math: ex2.approx)
+  return v * (v > 0.f ? 1.f - e : e);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(v, 0.f);
     case ACT_LEAKY: return v > 0.f ? v : 0.2f * v;                       // RELU_LEAK = 0.2 (unet_simple.py:10)
     case ACT_SILU: return v / (1.f + __expf(-v));
-    case ACT_GELU: return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));  // nn.GELU() = erf form
+    case ACT_GELU: return gelu_fast(v);  // nn.GELU() = erf form
     default: return v;
   }
 }
@@ -186,6 +204,20 @@ __device__ __forceinline__ uint32_t drop_keep_bits8(const DropCfg& d, const Drop
     bits |= (u16 >= d.thresh ? 1u : 0u) << j;
   }
   return bits;
+}
+
+// the same masks applied in place: v[j] = keep_j ? v[j] * scale : 0 for elements [e, e + 8) -- each 16-bit field is compared
+// and selected directly (no bit vector in between: 4 instead of 7 instructions per element in the issue-bound epilogues)
+__device__ __forceinline__ void drop_apply8(const DropCfg& d, const DropRow& dr, uint64_t e, float* v) {
+  Philox ph(rng_seed(d.seed, d.seed_ptr));
+  const uint64_t g = (dr.base + e) >> 3;
+  const uint4 r = ph((uint32_t)g, (uint32_t)(g >> 32), dr.stream, d.stream_hi_site);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = (w[j] & 0xFFFFu) >= d.thresh ? v[2 * j] * d.scale : 0.f;
+    v[2 * j + 1] = (w[j] >> 16) >= d.thresh ? v[2 * j + 1] * d.scale : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------- 16-bit packing

@@ -181,15 +181,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
             o[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a.z, b.z);
             o[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a.w, b.w);
           }
+          if (p.act == ACT_GELU) {  // (branch hoisted out of the element loop: the shipped SimpleConvNet is all GELU)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = apply_act(o[j], p.act);
+            for (int j = 0; j < 32; ++j) o[j] = gelu_fast(o[j]);
+          } else if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = apply_act(o[j], p.act);
+          }
           if (thresh) {  // element order of the NHWC tensor [row][y][x][64]: the masks of the mma.sync path
             const DropRow dr = drop_row(p.drop, call * p.G + img[u], (uint64_t)p.H * p.W * BN);
 #pragma unroll
             for (int cs = 0; cs < 32; cs += 8) {
-              const uint32_t keep = drop_keep_bits8(p.drop, dr, (uint64_t)(yy[u] * p.W + xx[u]) * BN + cbeg + cs);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[cs + j] = ((keep >> j) & 1u) ? o[cs + j] * dscale : 0.f;
+              drop_apply8(p.drop, dr, (uint64_t)(yy[u] * p.W + xx[u]) * BN + cbeg + cs, o + cs);
             }
           }
           if (p.res) {

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(co
           for (int j = 0; j < 32; ++j) y[j] = y[j] / (1.f + __expf(-y[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = 0.5f * y[j] * (1.f + erf_fast(y[j] * 0.70710678118654752f));
+          for (int j = 0; j < 32; ++j) y[j] = gelu_fast(y[j]);
         }
         if (thresh) {
 #pragma unroll
