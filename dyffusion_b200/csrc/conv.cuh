@@ -110,7 +110,8 @@ struct UpConvParams {
 bool conv_up_shape_ok(int C0, int C1, int Cout, int H, int W);
 size_t conv_up_weight_elems(int Cin, int Cout);
 #define DYF_UP_VARIANTS 9
-int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s);
+// nearest = 1: nn.Upsample(scale_factor=2, mode="nearest") instead of the clamped bilinear x2 (the SST Unet's up blocks)
+int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s, int nearest = 0);
 int launch_conv_up(const UpConvParams& p, cudaStream_t stream);
 
 // ---- spring-mesh layers on flat padded rasters (conv_flat.cu)

@@ -389,14 +389,16 @@ __global__ void __launch_bounds__(256) compose_up_kernel(const float* __restrict
 }
 // 1-D composite maps by simulating the reference ops on basis vectors: M[a][d][k] = coefficient of w[k] * x[i + d - 1]
 // in output 2i + a of (zero-padded 3-tap conv) o (clamped bilinear x2), for i at the start / interior / end of the axis.
-void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3]) {
+void axis_maps(int where /*0 first, 1 interior, 2 last*/, float M[2][3][3], int nearest) {
   const int L = 5, i = where == 0 ? 0 : where == 1 ? 2 : L - 1;
   for (int a = 0; a < 2; ++a)
     for (int d = 0; d < 3; ++d)
       for (int k = 0; k < 3; ++k) {
         const int src = i + d - 1, r = 2 * i + a + k - 1;  // source pixel, upsampled position read by tap k
         double v = 0.0;
-        if (src >= 0 && src < L && r >= 0 && r < 2 * L) {
+        if (nearest) {  // upsampled position r is a copy of source pixel r >> 1
+          if (src >= 0 && src < L && r >= 0 && r < 2 * L && (r >> 1) == src) v = 1.0;
+        } else if (src >= 0 && src < L && r >= 0 && r < 2 * L) {
           const int q = r >> 1;
           const int lo = r & 1 ? q : (q > 0 ? q - 1 : 0), hi = r & 1 ? (q + 1 < L ? q + 1 : L - 1) : q;
           const double wlo = r & 1 ? 0.75 : 0.25, whi = 1.0 - wlo;
@@ -443,9 +445,9 @@ size_t conv_up_weight_elems(int Cin, int Cout) { return (size_t)4 * Cout * Cin *
 // w: conv weight fp32 [Cout, Cin, 3, 3].  Fills the nine composite variants as tcgen05 stage tiles: interior, first row,
 // last row, first column, last column, then the corners (top-left, top-right, bottom-left, bottom-right).
 // `scratch` must hold 4*Cout*Cin*9 floats.
-int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s) {
+int launch_compose_up(const float* w, int Cout, int Cin, act_t* const* w_variants, float* scratch, cudaStream_t s, int nearest) {
   float ax[3][2][3][3];
-  for (int k = 0; k < 3; ++k) axis_maps(k, ax[k]);
+  for (int k = 0; k < 3; ++k) axis_maps(k, ax[k], nearest);
   const long long total = (long long)4 * Cout * Cin;
   const int vks[DYF_UP_VARIANTS] = {1, 0, 2, 1, 1, 0, 0, 2, 2}, hks[DYF_UP_VARIANTS] = {1, 1, 1, 0, 2, 0, 2, 0, 2};
   for (int v = 0; v < DYF_UP_VARIANTS; ++v) {

@@ -30,6 +30,7 @@ struct ConvLayer {
   int K = 0, Kpad = 0;
   size_t wq_off = 0;                          // offset (elements) into Net::wq (bf16 packed weights)
   int xmap_cols = 0;                            // > 0: 1x1 conv over a column subset of its input (Net::ro_xmap), output width
+  int up_nearest = 0;                           // fused upsample + conv (up_off): the upsample is nearest-neighbour, not bilinear
   int convt_z = 0;                              // weight = ConvTranspose2d [Cin, Cout/16, 4, 4] re-laid out as a 1x1 conv
   int comp_s2d = 0;                             // composite expressed as 3x3/s1 over the space-to-depth packed input
   int flops_cin = 0;                            // channels to count per tap in FLOP accounting (0 = Cin)

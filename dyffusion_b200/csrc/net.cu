@@ -594,14 +594,23 @@ int Net::build_unet_resnet() {
     x = attention_block(P + ".2", x, dout, true, site);
     const bool up = l < nres - 1 && !d.keep_spatial_dims;
     int in = x;
-    if (up) {  // nn.Upsample(scale_factor=2, mode="nearest") + Conv3x3 (:16-19)
+    // nn.Upsample(scale_factor=2, mode="nearest") + Conv3x3 (:16-19): one composite tcgen05 conv on the low-resolution grid
+    // (conv_up.cu with nearest-neighbour composite weights: no upsampled tensor) when the grid is >= 16 x 16
+    const bool fuse_up = up && conv_up_shape_ok(dout, 0, din, bufs[x].H, bufs[x].W) && !getenv("DYF_DISABLE_UPFUSE") &&
+                         !getenv("DYF_DISABLE_UMMA");
+    if (up && !fuse_up) {
       in = add_buf(bufs[x].H * 2, bufs[x].W * 2, dout);
       Op u{}; u.type = OP_UPSAMPLE; u.in0 = x; u.in1 = BUF_NONE; u.out = in; u.c0 = dout; u.c1 = 0; u.scale = 2; u.bilinear = 0;
       ops.push_back(u);
     }
     int li = add_conv(up ? P + ".3.1" : P + ".3", dout, din, 3, 1, 1);
-    int y = add_buf(bufs[in].H, bufs[in].W, din);
-    Op o{}; o.type = OP_CONV; o.in0 = in; o.out = y; o.layer = li; o.act = ACT_NONE;
+    int y = add_buf(bufs[in].H * (fuse_up ? 2 : 1), bufs[in].W * (fuse_up ? 2 : 1), din);
+    Op o{}; o.type = fuse_up ? OP_CONV_UP : OP_CONV; o.in0 = in; o.in1 = BUF_NONE; o.out = y; o.layer = li; o.act = ACT_NONE;
+    if (fuse_up) {
+      o.c0 = dout; o.c1 = 0;
+      convs[li].up_nearest = 1;
+      for (int v = 0; v < DYF_UP_VARIANTS; ++v) { convs[li].up_off[v] = (long long)wu_elems; wu_elems += conv_up_weight_elems(dout, din); }
+    }
     ops.push_back(o);
     x = y;
   }
@@ -660,7 +669,7 @@ int Net::finalize(cudaStream_t s) {
       DYF_CUDA_OK(cudaMalloc(&scratch, conv_up_weight_elems(c.Cin, c.Cout) * sizeof(float)));
       act_t* variants[DYF_UP_VARIANTS];
       for (int v = 0; v < DYF_UP_VARIANTS; ++v) variants[v] = wq_umma + c.up_off[v];
-      int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, scratch, s);
+      int ru = launch_compose_up(packed + params[c.w].off, c.Cout, c.Cin, variants, scratch, s, c.up_nearest);
       if (ru) return ru;
       DYF_CUDA_OK(cudaStreamSynchronize(s));
       DYF_CUDA_OK(cudaFree(scratch));
