@@ -15,6 +15,11 @@ static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+bool pdl_enabled(int family) {
+  static const bool on = getenv("DYF_DISABLE_PDL") == nullptr;
+  static const int mask = getenv("DYF_PDL_MASK") ? atoi(getenv("DYF_PDL_MASK")) : 0xB;  // (GroupNorm: see DESIGN.md)
+  return on && ((mask >> family) & 1);
+}
 uint64_t launch_counter() { return g_launches.load(); }
 
 // ---- NVTX ranges around network calls / sampler runs (nvtx3 is header-only and resolves the tool at run time)
@@ -220,6 +225,12 @@ int dyf_sampler_create(dyf_net* forecaster, dyf_net* interpolator, const dyf_sam
 }
 
 void dyf_sampler_destroy(dyf_sampler* s) { delete reinterpret_cast<Sampler*>(s); }
+
+int dyf_sampler_graph_replays(const dyf_sampler* s, uint64_t* replays) {
+  if (!s || !replays) { set_error("bad argument"); return DYF_ERR_ARG; }
+  *replays = reinterpret_cast<const Sampler*>(s)->graph_replays;
+  return DYF_OK;
+}
 
 int dyf_sampler_workspace_bytes(const dyf_sampler* s, int32_t rows, size_t* bytes) {
   if (!s || !bytes || rows <= 0) { set_error("bad argument"); return DYF_ERR_ARG; }

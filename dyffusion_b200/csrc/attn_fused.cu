@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(FTHREADS) linattn_ctx_fused_kernel(const LinAt
   const int row = blockIdx.y, chunk = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, h = warp & 3, ph = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
+  pdl_trigger();
   load_weight_rows<2 * HID, C>(p.w_qkv + (size_t)HID * p.ldw, p.ldw, sW);  // k and v rows of to_qkv.weight [384][C]
+  pdl_wait();  // (the weights are static: staged while the previous kernel drains; x is its output)
   const int c_beg = chunk * p.chunk_pix, c_end = min(p.n, c_beg + p.chunk_pix);
 
   float ctx[2][4][4];       // [d block of 16][e block of 8][frag]: rows d = 16 mb + g (+8), cols e = 8 eb + 2t (+1)
@@ -274,6 +276,8 @@ __global__ void __launch_bounds__(FTHREADS) linattn_ctx_fused_kernel(const LinAt
 // ctx = sum_chunks e^(m_c - m) ctx_c / (sum_chunks e^(m_c - m) l_c) / n per (row, head), stored transposed ([e][d], d
 // contiguous: the B operand of pass 2) as 16-bit values in the first bytes of the row's partial area
 __global__ void __launch_bounds__(256) linattn_ctx_combine_kernel(const LinAttnFusedParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.y, hh = blockIdx.x;
   const float* base = p.part + ((size_t)row * p.chunks * HEADS + hh) * PART;
   act_t* out = p.ctx16 + ((size_t)row * HEADS + hh) * DH * DH;
@@ -304,8 +308,10 @@ __global__ void __launch_bounds__(FTHREADS) linattn_out_fused_kernel(const LinAt
   act_t* sX = sC + HEADS * DH * LDC;
   const int row = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  pdl_trigger();
   load_weight_rows<HID, C>(p.w_qkv, p.ldw, sWq);       // q rows of to_qkv.weight
   load_weight_rows<C, HID>(p.w_out, p.ldw_out, sWo);   // to_out.weight [C][128]
+  pdl_wait();  // (static weights staged before the wait; the context and x are outputs of the previous kernels)
   {  // ctx^T of the row (linattn_ctx_combine_kernel): [4 * 32 e][32 d] -> padded rows
     const act_t* src = p.ctx16 + (size_t)row * HEADS * DH * DH;
     for (int i = threadIdx.x; i < HEADS * DH * (DH / 8); i += FTHREADS) {
@@ -443,6 +449,8 @@ __global__ void __launch_bounds__(FTHREADS) linattn_out_fused_kernel(const LinAt
 // probabilities, then the probabilities re-packed as A fragments of O = P V.  NP = keys rounded up to a multiple of 16.
 template <int NP>
 __global__ void __launch_bounds__(FTHREADS) attention_mma_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int LDQ = DH + 8, LDV = NP + 8, NB = NP / 8;
   act_t* sQ = reinterpret_cast<act_t*>(smem_raw);   // [NP][LDQ], pre-scaled by dh^-0.5
@@ -584,8 +592,7 @@ int launch_attention_mma_t(const AttnParams& p, cudaStream_t s) {
     configured = true;
   }
   ProfScope prof(s, KC_ATTENTION, 4.0 * p.rows * p.heads * (double)p.n * p.n * DH);
-  attention_mma_kernel<NP><<<dim3(p.heads, p.rows), FTHREADS, smem, s>>>(p);
-  DYF_LAUNCH_OK("attention_mma_kernel");
+  DYF_LAUNCH_PDL(3, "attention_mma_kernel", attention_mma_kernel<NP>, dim3(p.heads, p.rows), dim3(FTHREADS), smem, s, p);
   return 0;
 }
 
@@ -604,15 +611,12 @@ int launch_fused_t(const LinAttnFusedParams& p, cudaStream_t s) {
   const double flops = 2.0 * p.rows * (double)p.n * (3.0 * HID * C + 2.0 * HEADS * DH * DH + (double)HID * C);
   const double bytes = 2.0 * p.rows * (double)p.n * C * 3.0;
   ProfScope prof(s, KC_ATTENTION, flops, bytes);
-  linattn_ctx_fused_kernel<C><<<dim3(p.chunks, p.rows), FTHREADS, smem1b, s>>>(p);
-  DYF_LAUNCH_OK("linattn_ctx_fused_kernel");
-  linattn_ctx_combine_kernel<<<dim3(HEADS, p.rows), 256, 0, s>>>(p);
-  DYF_LAUNCH_OK("linattn_ctx_combine_kernel");
+  DYF_LAUNCH_PDL(3, "linattn_ctx_fused_kernel", linattn_ctx_fused_kernel<C>, dim3(p.chunks, p.rows), dim3(FTHREADS), smem1b, s, p);
+  DYF_LAUNCH_PDL(3, "linattn_ctx_combine_kernel", linattn_ctx_combine_kernel, dim3(HEADS, p.rows), dim3(256), 0, s, p);
   // CTAs per row: enough of them for ~4 resident waves, each walking several tiles with the weights staged once
   const int ntiles = cdiv(p.n, TP);
   const int per_row = std::max(1, std::min(ntiles, cdiv(4 * 2 * 148, p.rows)));
-  linattn_out_fused_kernel<C><<<dim3(per_row, p.rows), FTHREADS, smem2, s>>>(p);
-  DYF_LAUNCH_OK("linattn_out_fused_kernel");
+  DYF_LAUNCH_PDL(3, "linattn_out_fused_kernel", linattn_out_fused_kernel<C>, dim3(per_row, p.rows), dim3(FTHREADS), smem2, s, p);
   return 0;
 }
 

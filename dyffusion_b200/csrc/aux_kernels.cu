@@ -491,6 +491,8 @@ constexpr int GNF_THREADS = 256, GNF_UNROLL = 4, GNF_SLABS = 8;
 #define GNF_AU 1
 #endif
 __global__ void __launch_bounds__(GNF_THREADS, GNF_MINB) groupnorm_fused_kernel(const GroupNormParams p, int CS, int slab_pix) {
+  pdl_trigger();
+  pdl_wait();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float s_part[GNF_THREADS][2];
@@ -1071,10 +1073,12 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(p.rows * CS)); cfg.blockDim = dim3(GNF_THREADS);
     cfg.dynamicSmemBytes = 2 * p.C * sizeof(float); cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see pdl_wait in common.cuh)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled(2) ? 2 : 1;
     DYF_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel, p, CS, per));
     count_launch();
     return 0;

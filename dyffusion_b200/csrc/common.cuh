@@ -63,6 +63,38 @@ struct ProfScope {
     ::dyf::count_launch();                                                                             \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels launched through DYF_LAUNCH_PDL may be scheduled while their predecessor on the stream is still draining: the block
+// scheduler places their CTAs as SMs free up, and their prologue (barrier init, TMEM allocation, static weight loads)
+// overlaps the predecessor's tail.  Rules every such kernel obeys: `pdl_trigger()` first thing (lets ITS successor do the same),
+// and EVERY thread executes `pdl_wait()` -- which returns once all predecessor grids have completed and flushed -- before its
+// first read or write of memory another kernel touches and before it exits (so completion stays transitive along the stream).
+// DYF_DISABLE_PDL=1 launches without the attribute (the wait is then a no-op).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled(int family = 0);  // family: 0 conv_umma, 1 conv_up, 2 GroupNorm, 3 attention (DYF_PDL_MASK, default all)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int family, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled(family) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define DYF_LAUNCH_PDL(family, what, kern, grid, block, smem, stream, ...)                                   \
+  do {                                                                                                 \
+    cudaError_t _e = ::dyf::launch_pdl(family, kern, grid, block, smem, stream, __VA_ARGS__);                \
+    if (_e != cudaSuccess) {                                                                           \
+      ::dyf::set_error(std::string("launch of ") + what + " failed: " + cudaGetErrorString(_e));       \
+      return -2;                                                                                       \
+    }                                                                                                  \
+    ::dyf::count_launch();                                                                             \
+  } while (0)
+
 // ---------------------------------------------------------------- activations (fp32 math)
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SILU = 3, ACT_GELU = 4 };
 

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(co
   constexpr int A_STAGE = S2TMA ? VREGION : TMA ? ((PIXT * 128 + 1023) / 1024) * 1024 : S::A_STAGE;
   constexpr int B_TAP = BN * CHK * 2;      // one tap of one chunk: [k8][BN rows][16 B]
   constexpr int B_STAGE = GT * B_TAP;      // a weight stage carries GT taps
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + AS * A_STAGE;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail; everything below touches its output
 
   // work item -> (n_tile, batch row, tile origin)
   auto decode = [&](int w, int& n_tile, int& row, int& oy0, int& ox0) {
@@ -622,9 +624,8 @@ int launch_t(const ConvParams& p, cudaStream_t stream, const CUtensorMap* views 
   const double flops = 2.0 * (double)p.M * p.Cout * G::TAPS * p.Cin_real;
   const double bytes = 2.0 * ((double)p.rows * p.Hi * (p.in_xmap ? p.Wo : p.Wi) * p.Cin + (double)p.M * p.Cout + (double)p.Cout * p.Kpad);
   ProfScope prof(stream, KC_CONV_UMMA, flops, bytes);
-  conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT><<<grid, cta_threads(TMA, MODE), smem, stream>>>(p, p.w_umma, tiles_x, tiles_y, n_tiles,
-                                                                                (int)work, tmap, tmap2, tmap3, tmap4, nch_split, wd);
-  DYF_LAUNCH_OK("conv_umma_kernel");
+  DYF_LAUNCH_PDL(0, "conv_umma_kernel", (conv_umma_kernel<BN, MODE, AS, BS, TMA, T, GT>), dim3(grid), dim3(cta_threads(TMA, MODE)), smem,
+                 stream, p, p.w_umma, tiles_x, tiles_y, n_tiles, (int)work, tmap, tmap2, tmap3, tmap4, nch_split, wd);
   return 1;
 }
 

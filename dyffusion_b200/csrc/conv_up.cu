@@ -324,6 +324,7 @@ __device__ __forceinline__ void up_phase(const UpConvParams& p, uint8_t* smem, u
 
 __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams p, const UpWork wk, int n_tiles,
                                                              const __grid_constant__ UpMaps maps) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   UBarriers* bars = reinterpret_cast<UBarriers*>(smem + BAR_OFF);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_up_kernel(const UpConvParams 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    if (phase == 0) pdl_wait();  // TMEM allocation and barrier init overlapped the previous kernel's tail
     const CUtensorMap* m0 = &maps.m[phase][0];
     const CUtensorMap* m1 = &maps.m[phase][1];
     // The work items of all phases form one round-robin sequence over the CTAs (concurrent CTAs work on neighbouring
@@ -495,8 +497,7 @@ int launch_conv_up(const UpConvParams& p, cudaStream_t stream) {
   const double flops = 2.0 * 4.0 * p.rows * p.H * p.W * p.Cout * 9.0 * Cin;  // = the reference conv on the upsampled grid
   const double bytes = 2.0 * ((double)p.rows * p.H * p.W * (Cin + 4.0 * p.Cout) + 36.0 * p.Cout * Cin);
   ProfScope prof(stream, KC_CONV_UP, flops, bytes);
-  conv_up_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p, wk, n_tiles, maps);
-  DYF_LAUNCH_OK("conv_up_kernel");
+  DYF_LAUNCH_PDL(1, "conv_up_kernel", conv_up_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, stream, p, wk, n_tiles, maps);
   return 0;
 }
 

@@ -155,6 +155,11 @@ struct Sampler {
     uint64_t kernels = 0;            // kernel launches inside the graph (for dyf_launch_count)
   };
   std::map<std::tuple<int, const void*, uint64_t>, GraphEntry> graphs;
+  // The legacy default stream (what PyTorch's current stream is unless the caller switches) cannot be captured: graph mode
+  // then runs on this sampler's own non-blocking stream, fenced against the caller's stream with events on both sides.
+  uint64_t graph_replays = 0;      // runs served by cudaGraphLaunch
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   ~Sampler();
   int plan();
   size_t workspace_bytes(int rows) const;
@@ -163,6 +168,8 @@ struct Sampler {
               const uint64_t* seed_dev, uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s);
   int run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, uint64_t row_offset,
           void* ws, size_t ws_bytes, cudaStream_t s);
+  int run_on(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed, uint64_t row_offset,
+             void* ws, size_t ws_bytes, cudaStream_t s);  // run() after the stream choice
 };
 
 bool profiling_enabled();          // abi.cu: per-launch event bracketing is on (incompatible with stream capture)

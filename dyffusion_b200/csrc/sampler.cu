@@ -1,6 +1,7 @@
 // The DYffusion sampling loop (reference: BaseDYffusion.sample_loop, src/diffusion/dyffusion.py:335-426) driven
 // natively: no Python between network calls, the two interpolator evaluations of a cold-sampling step batched into
 // one launch sequence (2R rows), the refinement calls batched as well, all on the caller's stream.
+#include <cstdio>
 #include <algorithm>
 #include <cmath>
 
@@ -101,6 +102,9 @@ Sampler::~Sampler() {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
   }
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_out) cudaEventDestroy(ev_out);
+  if (side_stream) cudaStreamDestroy(side_stream);
 }
 
 __global__ void store_seed_kernel(uint64_t* dst, uint64_t seed) { *dst = seed; }
@@ -224,7 +228,29 @@ int Sampler::enqueue(int rows, const float* ic, const float* stat, float* preds,
 }
 
 int Sampler::run(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed,
-                 uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s) {
+                 uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t caller) {
+  cudaStream_t s = caller;
+  const bool graph_mode = d.cuda_graph && !profiling_enabled();
+  if (graph_mode && (caller == nullptr || caller == cudaStreamLegacy)) {  // un-capturable stream: run on the side stream
+    if (!side_stream) {
+      DYF_CUDA_OK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+      DYF_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+      DYF_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    }
+    DYF_CUDA_OK(cudaEventRecord(ev_in, caller));
+    DYF_CUDA_OK(cudaStreamWaitEvent(side_stream, ev_in, 0));
+    s = side_stream;
+  }
+  const int rc_run = run_on(rows, ic, stat, preds, x0_out, seed, row_offset, ws, ws_bytes, s);
+  if (s != caller) {  // (also after an error: whatever was enqueued on the side stream stays ordered before the caller's next work)
+    DYF_CUDA_OK(cudaEventRecord(ev_out, s));
+    DYF_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
+  }
+  return rc_run;
+}
+
+int Sampler::run_on(int rows, const float* ic, const float* stat, float* preds, float* x0_out, uint64_t seed,
+                    uint64_t row_offset, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < workspace_bytes(rows)) { set_error("sampler workspace too small"); return DYF_ERR_ARG; }
   if ((d.static_channels > 0) != (stat != nullptr)) { set_error("static_condition does not match static_channels"); return DYF_ERR_ARG; }
   if (row_offset + (uint64_t)rows > 0xFFFFFFFFull) { set_error("row_offset out of range"); return DYF_ERR_ARG; }
@@ -259,6 +285,7 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
   if (g.exec) {
     DYF_CUDA_OK(cudaGraphLaunch(g.exec, s));
     count_launch((int)g.kernels);
+    ++graph_replays;
   } else if (g.failed || g.runs == 0) {
     // first run of this key: plain launches (builds the epilogue tables, tensor maps and function attributes that the
     // capture below must not have to create)
@@ -279,6 +306,7 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
           g.exec = exec; g.graph = graph; g.genF = F->generation; g.genI = I->generation;
           g.kernels = launch_counter() - l0;
           DYF_CUDA_OK(cudaGraphLaunch(g.exec, s));
+          ++graph_replays;
         } else {
           cudaGraphDestroy(graph);
         }
@@ -287,6 +315,8 @@ int Sampler::run(int rows, const float* ic, const float* stat, float* preds, flo
       }
     }
     if (!g.exec) {  // capture refused (e.g. a cache had to allocate): remember, clear the sticky error, launch plainly
+      if (getenv("DYF_DEBUG_GRAPH"))
+        fprintf(stderr, "[dyf] graph capture failed (rows=%d row_offset=%u rc=%d): %s | %s\n", rows, (unsigned)row_offset, rc, cudaGetErrorString(ce), get_error());
       cudaGetLastError();
       g.failed = true;
       rc = enqueue(rows, s_ic, s_st, s_preds, s_x0, seed, seed_dev, row_offset, loop_ws, loop_ws_bytes, s);

@@ -77,6 +77,7 @@ def _load() -> C.CDLL:
         "dyf_sampler_workspace_bytes": (C.c_int, [vp, i32, C.POINTER(sz)]),
         "dyf_sampler_num_outputs": (C.c_int, [vp, C.POINTER(i32), C.POINTER(C.c_double), i32]),
         "dyf_sampler_run": (C.c_int, [vp, i32, vp, vp, vp, vp, u64, u64, vp, sz, vp]),
+        "dyf_sampler_graph_replays": (C.c_int, [vp, C.POINTER(u64)]),
         "dyf_debug_dropout_mask": (C.c_int, [u64, u64, C.c_uint32, C.c_float, C.c_int64, vp, vp]),
         "dyf_ensemble_metrics_workspace_bytes": (C.c_int, [i32, C.c_int64, C.c_int64, C.POINTER(sz)]),
         "dyf_ensemble_metrics": (C.c_int, [vp, vp, i32, C.c_int64, C.c_int64, vp, vp, vp, sz, vp]),
@@ -105,6 +106,7 @@ EXPORTED = ["dyf_abi_version", "dyf_last_error", "dyf_act_dtype", "dyf_nvtx_enab
             "dyf_net_set_param", "dyf_net_finalize", "dyf_net_num_params", "dyf_net_param_key", "dyf_net_param_shape",
             "dyf_net_workspace_bytes", "dyf_net_forward", "dyf_net_forward_srcs", "dyf_sampler_create",
             "dyf_sampler_destroy", "dyf_sampler_workspace_bytes", "dyf_sampler_num_outputs", "dyf_sampler_run",
+            "dyf_sampler_graph_replays",
             "dyf_debug_dropout_mask", "dyf_profile_enable", "dyf_profile_filter", "dyf_profile_read",
             "dyf_ensemble_metrics_workspace_bytes", "dyf_ensemble_metrics", "dyf_boundary_conditions_navier_stokes",
             "dyf_boundary_conditions_spring_mesh", "dyf_window_gather", "dyf_adamw_workspace_bytes",
@@ -354,6 +356,12 @@ class SamplerHandle:
                 C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint64(int(row_offset)), C.c_void_p(ws.data_ptr()), ws.numel(),
                 C.c_void_p(_stream_ptr())))
         return preds, x0
+
+    def graph_replays(self) -> int:
+        """Runs of this sampler that were served by replaying a captured CUDA graph (measurement hook)."""
+        n = C.c_uint64(0)
+        _check(LIB.dyf_sampler_graph_replays(self._h, C.byref(n)))
+        return int(n.value)
 
 
 def debug_dropout_mask(seed: int, stream: int, site: int, p: float, n: int, device="cuda") -> torch.Tensor:

@@ -182,6 +182,10 @@ int dyf_sampler_num_outputs(const dyf_sampler* s, int32_t* n_outputs, double* ke
 int dyf_sampler_run(dyf_sampler* s, int32_t rows, const float* ic, const float* static_cond, float* preds,
                     float* x0_hat_out, uint64_t seed, uint64_t row_offset, void* workspace, size_t workspace_bytes,
                     void* stream);
+/* Measurement hook (no reference counterpart): how many `dyf_sampler_run` calls of this sampler were served by replaying a
+ * captured CUDA graph (0 while `cuda_graph` is off, profiling is on, or every capture was refused).  A caller on the legacy
+ * default stream -- which cannot be captured -- is served from the sampler's own stream, fenced with events on both sides. */
+int dyf_sampler_graph_replays(const dyf_sampler* s, uint64_t* replays);
 /* NVTX ranges ("dyf.net.forward <arch> rows=..", "dyf.sampler.run") around every network call / sampler run, for
  * nsys / ncu timelines (off by default; also switched on by the environment variable DYF_NVTX=1). */
 int dyf_nvtx_enable(int32_t on);

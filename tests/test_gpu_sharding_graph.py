@@ -62,6 +62,27 @@ def test_cuda_graph_replay_equals_plain_launches(dataset, horizon, rows):
     assert not torch.equal(outs[2]["t1_preds"], outs[3]["t1_preds"])  # replays draw new dropout masks (seed in device memory)
     sampler = next(iter(graph._native_cache.values()))
     assert sampler.cuda_graph
+    # runs 2-4 really went through cudaGraphLaunch (on PyTorch's default stream too: the legacy stream cannot be captured, the
+    # sampler then runs on its own stream fenced with events) and none of the plain sampler's did
+    assert sampler.graph_replays() == 3
+    assert next(iter(plain._native_cache.values())).graph_replays() == 0
+
+
+def test_graph_mode_on_a_side_stream_and_on_the_default_stream_agree():
+    from tests.gpu_helpers import build_dyffusion
+    dyf = build_dyffusion("spring", horizon=5, cuda_graph=True)
+    ic, static = H.sampler_case_inputs("graph2", "spring", 4)
+    ic, static = ic.cuda(), static.cuda()
+    ref = [_sample(dyf, ic, static, seed) for seed in (1, 2, 3)]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = [_sample(dyf, ic, static, seed) for seed in (1, 2, 3)]
+    side.synchronize()
+    for a, b in zip(ref, out):
+        for k in a:
+            assert torch.equal(a[k], b[k])
 
 
 def test_weights_changed_in_place_are_repacked():
