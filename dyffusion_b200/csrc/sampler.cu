@@ -276,7 +276,15 @@ int Sampler::run_on(int rows, const float* ic, const float* stat, float* preds, 
   void* loop_ws = base + staged;
   const size_t loop_ws_bytes = ws_bytes - used - staged;
 
-  GraphEntry& g = graphs[std::make_tuple(rows, (const void*)base, row_offset)];
+  const auto gkey = std::make_tuple(rows, (const void*)base, row_offset);
+  if (graphs.size() >= 32 && !graphs.count(gkey)) {  // bound the cache (a caller sweeping batch sizes): drop everything, re-capture
+    for (auto& kv : graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    graphs.clear();
+  }
+  GraphEntry& g = graphs[gkey];
   if (g.exec && (g.genF != F->generation || g.genI != I->generation)) {  // weights / tables were rebuilt: re-capture
     cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph);
     g = GraphEntry{};
