@@ -490,7 +490,8 @@ constexpr int GNF_THREADS = 256, GNF_UNROLL = 4, GNF_SLABS = 8;
 #ifndef GNF_AU
 #define GNF_AU 1
 #endif
-__global__ void __launch_bounds__(GNF_THREADS, GNF_MINB) groupnorm_fused_kernel(const GroupNormParams p, int CS, int slab_pix) {
+template <int AU, int MINB>  // AU = pixels in flight per thread in the apply pass, MINB = CTAs per SM the register budget allows
+__global__ void __launch_bounds__(GNF_THREADS, MINB) groupnorm_fused_kernel(const GroupNormParams p, int CS, int slab_pix) {
   pdl_trigger();
   pdl_wait();
   namespace cg = cooperative_groups;
@@ -584,7 +585,6 @@ __global__ void __launch_bounds__(GNF_THREADS, GNF_MINB) groupnorm_fused_kernel(
   const DropRow dr = drop_row(p.drop, r, (uint64_t)p.HW * p.C);
   act_t* y = p.y + (size_t)r * p.HW * p.C + (ch << 3);
   const act_t* res = p.res ? p.res + (size_t)r * p.HW * p.res_ld + (ch << 3) : nullptr;
-  constexpr int AU = GNF_AU;  // pixels in flight per thread in the apply pass
   for (px = p_beg + lane_px; px < p_end; px += AU * pstep) {
     uint4 u[AU], rr[AU];
 #pragma unroll
@@ -1079,7 +1079,9 @@ int launch_groupnorm(const GroupNormParams& p, cudaStream_t s) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see pdl_wait in common.cuh)
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled(2) ? 2 : 1;
-    DYF_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel, p, CS, per));
+    // one pixel in flight per thread and 40 registers (6 CTAs / SM, no spills): measured against 2 and 4 pixels in flight
+    // (2.36 - 2.72 ms per 304-row SST forward: spills) and against 32 registers / 8 CTAs (2.07 ms, 24 bytes of spills): 2.04 ms
+    DYF_CUDA_OK(cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel<1, 6>, p, CS, per));
     count_launch();
     return 0;
   }
