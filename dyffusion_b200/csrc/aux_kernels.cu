@@ -133,18 +133,15 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const
 // (zero outside the image, c >= C_in, kx = 7): the horizontal taps of a 7x7 stem live in the channel axis, so the conv is
 // seven VERTICAL taps over 64 channels on the tcgen05 halo-patch kernel (conv_umma.cu, S1K7V).  "data+noise" conditioning is
 // applied per source element with the element-keyed Philox stream of pack_kernel (the seven copies of a pixel agree).
-__global__ void __launch_bounds__(256) pack_xim2col_kernel(const PackParams p, const S2dChannels ch) {
-  const unsigned per_row = (unsigned)(p.Ho * p.Wo);
-  const RowPos rp = row_pos(per_row);
-  if (rp.i >= per_row) return;
-  const int y = (int)(rp.i / (unsigned)p.Wo), x = (int)(rp.i - (unsigned)y * p.Wo);
-  const int r = (int)rp.r;
-  const int rs = r % p.src_rows;
+// One CTA per image row: every source pixel is gathered, noised and packed to 8 x 16 bit ONCE into shared memory (with the
+// three zero pixels of padding on either side); an output pixel is then seven 128-bit copies of its neighbours + one of zeros.
+__global__ void __launch_bounds__(128) pack_xim2col_kernel(const PackParams p, const S2dChannels ch) {
+  extern __shared__ __align__(16) uint4 s_px[];  // [Wi + 6]
+  const unsigned y = blockIdx.x % (unsigned)p.Ho, r = blockIdx.x / (unsigned)p.Ho;
+  const unsigned rs = r % (unsigned)p.src_rows;
   const size_t plane = (size_t)p.Hi * p.Wi;
-  uint4* o = reinterpret_cast<uint4*>(p.out + ((size_t)rp.r * per_row + rp.i) * 64);
-#pragma unroll
-  for (int kx = 0; kx < 7; ++kx) {
-    const int xs = x + kx - 3;
+  for (int x = threadIdx.x; x < p.Wi + 6; x += blockDim.x) {
+    const int xs = x - 3;
     float v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -152,7 +149,7 @@ __global__ void __launch_bounds__(256) pack_xim2col_kernel(const PackParams p, c
       if (c < ch.n && xs >= 0 && xs < p.Wi) {
         val = __ldg(ch.plane[c] + (size_t)rs * ch.row_stride[c] + (size_t)y * p.Wi + xs);
         if (c >= p.noise_c0 && c < p.noise_c1) {
-          const uint32_t jc = (uint32_t)r / p.rng_rows, rr = (uint32_t)r - jc * p.rng_rows + p.row_off;
+          const uint32_t jc = r / p.rng_rows, rr = r - jc * p.rng_rows + p.row_off;
           const uint64_t e = ((uint64_t)rr * (p.noise_c1 - p.noise_c0) + (c - p.noise_c0)) * plane + (size_t)y * p.Wi + xs;
           Philox ph(rng_seed(p.seed, p.seed_ptr));
           uint4 rn = ph((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p.stream + jc, 0x4e4f4953u);
@@ -161,9 +158,14 @@ __global__ void __launch_bounds__(256) pack_xim2col_kernel(const PackParams p, c
       }
       v[c] = val;
     }
-    o[kx] = pack8(v);
+    s_px[x] = pack8(v);
   }
-  o[7] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  uint4* const orow = reinterpret_cast<uint4*>(p.out + ((size_t)blockIdx.x * p.Wo) * 64);
+  for (int i = threadIdx.x; i < p.Wo * 8; i += blockDim.x) {  // 16-byte unit i of the row: pixel i / 8, tap i % 8 (coalesced)
+    const int x = i >> 3, kx = i & 7;
+    orow[i] = kx < 7 ? s_px[x + kx] : make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // 7x7 stem filter fp32 [O][C][7][7] -> [O][64][7]: (kx * 8 + c, ky), zero for the unused slots (the weight of the conv over
@@ -990,7 +992,7 @@ int launch_pack(const PackParams& p, cudaStream_t s) {
     }
     if (p.bilinear || p.Hi != p.Ho || p.Wi != p.Wo) { set_error("pack x-im2col: no resize"); return -1; }
     ProfScope prof(s, KC_PACK);
-    pack_xim2col_kernel<<<row_grid(p.rows, (long long)p.Ho * p.Wo), 256, 0, s>>>(q, ch);
+    pack_xim2col_kernel<<<(unsigned)(p.rows * p.Ho), 128, (size_t)(p.Wi + 6) * sizeof(uint4), s>>>(q, ch);
     DYF_LAUNCH_OK("pack_xim2col_kernel");
     return 0;
   }
