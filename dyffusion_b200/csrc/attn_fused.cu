@@ -281,16 +281,29 @@ __global__ void __launch_bounds__(256) linattn_ctx_combine_kernel(const LinAttnF
   const int row = blockIdx.y, hh = blockIdx.x;
   const float* base = p.part + ((size_t)row * p.chunks * HEADS + hh) * PART;
   act_t* out = p.ctx16 + ((size_t)row * HEADS + hh) * DH * DH;
+  constexpr int MAXC = 8;  // linattn_fused_chunks() <= 8: all loads of an element are issued before the first use
   for (int i = threadIdx.x; i < DH * DH; i += blockDim.x) {
     const int d = i / DH, e = i - d * DH;
-    float mm = -INFINITY;
-    for (int c = 0; c < p.chunks; ++c) mm = fmaxf(mm, base[(size_t)c * HEADS * PART + d]);
-    float num = 0.f, den = 0.f;
-    for (int c = 0; c < p.chunks; ++c) {
+    float mc[MAXC], lc[MAXC], xc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
       const float* pc = base + (size_t)c * HEADS * PART;
-      const float wgt = pc[d] == -INFINITY ? 0.f : __expf(pc[d] - mm);
-      num += wgt * pc[2 * DH + d * DH + e];
-      den += wgt * pc[DH + d];
+      const bool on = c < p.chunks;
+      mc[c] = on ? __ldg(pc + d) : -INFINITY;
+      lc[c] = on ? __ldg(pc + DH + d) : 0.f;
+      xc[c] = on ? __ldg(pc + 2 * DH + d * DH + e) : 0.f;
+    }
+    float mm = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) mm = fmaxf(mm, mc[c]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {  // (same order and arithmetic as a loop over p.chunks: absent chunks add exact zeros)
+      if (c < p.chunks) {
+        const float wgt = mc[c] == -INFINITY ? 0.f : __expf(mc[c] - mm);
+        num += wgt * xc[c];
+        den += wgt * lc[c];
+      }
     }
     out[e * DH + d] = f2act(num / (den * (float)p.n));
   }
