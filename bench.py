@@ -376,7 +376,7 @@ def run_engine(args):
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
                          "algorithmic_bytes_per_launch": d["bytes"] / max(1, d["launches"]), "peak_source": pk["source"],
                          "launches": d["launches"], "avg_launch_ms": d["ms"] / max(1, d["launches"]),
-                         "share_of_kernel_time": d["ms"] / total_kernel_ms if total_kernel_ms else None,
+                         "share_of_kernel_time": (d["ms"] / args.steps) / total_kernel_ms if total_kernel_ms else None,
                          "timed": f"live: {args.steps} plain-launch steps right after the timed region with CUDA events around the "
                                   "launches of this class only (the timed region itself replays the sampler's CUDA graph)",
                          "ms_per_step_during_measurement": ms_plain / args.steps,
