@@ -124,8 +124,7 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const PackParams p, const
   for (int i = 0; i < 16; ++i)
     v[i] = i < N ? (w00 * g[i][0] + w01 * g[i][1] + w10 * g[i][2] + w11 * g[i][3]) : i == N ? 1.f : 0.f;
   uint4* o = reinterpret_cast<uint4*>(p.out + blk * 64 + sub * 16);
-  o[0] = pack8(v);
-  o[1] = pack8(v + 8);
+  st_global_256(o, pack8(v), pack8(v + 8));  // 32 bytes per thread, 32-byte aligned
 }
 
 // ------------------------------------------------------------------------------------------------ pack, x-im2col

@@ -289,6 +289,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
 }
 
+// 256-bit global store (sm_100: STG.E.256) of 16 consecutive 16-bit values to a 32-byte-aligned address: an epilogue thread
+// that owns 32+ contiguous bytes writes whole 32-byte sectors per request instead of two half-sector requests
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+#endif
+
+#ifdef __CUDACC__
+// ... and the matching 256-bit read-only load (LDG.E.256.CONSTANT), 32-byte-aligned address
+__device__ __forceinline__ void ld_global_nc_256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(ptr));
+}
+#endif
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace dyf

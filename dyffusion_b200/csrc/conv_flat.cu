@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
         if (p.res && valid[u]) {  // residual = this layer's input at the same pixel = the same raster position
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + ((size_t)call * p.PC_in + lp[u]) * BN + u_col[u]);
 #pragma unroll
-          for (int cs = 0; cs < 4; ++cs) rsd[u][cs] = __ldg(rp + cs);
+          for (int cs = 0; cs < 4; cs += 2) ld_global_nc_256(rp + cs, rsd[u][cs], rsd[u][cs + 1]);
         }
       }
       mbar_wait(smem_u32(&bars->acc_full[acc]), (it >> 1) & 1);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_flat_net_kernel(const __grid_
           } else {
             uint4* op = reinterpret_cast<uint4*>(p.out + ((size_t)call * p.PC_out + (size_t)img[u] * p.PI_out + yy[u] * p.S_out + xx[u]) * BN + cbeg);
 #pragma unroll
-            for (int cs = 0; cs < 4; ++cs) op[cs] = pack8(o + 8 * cs);
+            for (int cs = 0; cs < 4; cs += 2) st_global_256(op + cs, pack8(o + 8 * cs), pack8(o + 8 * cs + 8));  // (rows of 128 B, cbeg % 32 == 0)
           }
         }
         __syncwarp();  // the next tcgen05.ld is warp-collective

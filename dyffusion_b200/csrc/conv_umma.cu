@@ -214,6 +214,8 @@ __global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(co
     const float slope = act == ACT_NONE ? 1.f : act == ACT_RELU ? 0.f : 0.2f;
     const uint32_t thresh = p.drop.thresh;
     const float dscale = p.drop.scale;
+    const bool wide_st = ((p.out_ld | p.out_coff) & 15) == 0;  // output rows and slices 32-byte aligned: 256-bit stores
+    const bool wide_res = p.res && (p.res_ld & 15) == 0;
     int it = 0, tab_key = -1, tab_buf = 0;
     for (int w0 = blockIdx.x * cw; w0 < num_work; w0 += gridDim.x * cw)
     for (int w = w0; w < min(w0 + cw, num_work); ++w, ++it) {
@@ -293,18 +295,38 @@ __global__ void __launch_bounds__(cta_threads(TMA, MODE), 1) conv_umma_kernel(co
         if (valid) {
           if (rrow) {
 #pragma unroll
-            for (int cs = 0; cs < 32; cs += 8) {
-              if (n_tile * BN + cg + cs < p.Cout) {
-                float f[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(rrow + cg + cs)), f);
+            for (int cs = 0; cs < 32; cs += 16) {
+              const int c0 = n_tile * BN + cg + cs;
+              uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+              if (wide_res && c0 + 16 <= p.Cout) {
+                ld_global_nc_256(rrow + cg + cs, r0, r1);
+              } else {
+                if (c0 < p.Cout) r0 = __ldg(reinterpret_cast<const uint4*>(rrow + cg + cs));
+                if (c0 + 8 < p.Cout) r1 = __ldg(reinterpret_cast<const uint4*>(rrow + cg + cs + 8));
+              }
+              float f[8];
+              if (c0 < p.Cout) {
+                unpack8(r0, f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[cs + j] += f[j];
+              }
+              if (c0 + 8 < p.Cout) {
+                unpack8(r1, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[cs + 8 + j] += f[j];
               }
             }
           }
 #pragma unroll
-          for (int cs = 0; cs < 32; cs += 8)
-            if (n_tile * BN + cg + cs < p.Cout) *reinterpret_cast<uint4*>(orow + cg + cs) = pack8(y + cs);
+          for (int cs = 0; cs < 32; cs += 16) {
+            const int c0 = n_tile * BN + cg + cs;
+            if (wide_st && c0 + 16 <= p.Cout) {
+              st_global_256(orow + cg + cs, pack8(y + cs), pack8(y + cs + 8));
+            } else {
+              if (c0 < p.Cout) *reinterpret_cast<uint4*>(orow + cg + cs) = pack8(y + cs);
+              if (c0 + 8 < p.Cout) *reinterpret_cast<uint4*>(orow + cg + cs + 8) = pack8(y + cs + 8);
+            }
+          }
         }
       }
       }

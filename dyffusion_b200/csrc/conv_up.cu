@@ -119,8 +119,17 @@ __device__ __forceinline__ void up_store(const UpConvParams& p, int img, int i, 
       for (int e = 0; e < 8; ++e) y[8 * g + e] = ((keep >> e) & 1u) ? y[8 * g + e] * p.drop.scale : 0.f;
     }
   }
+  const bool wide_st = (p.out_ld & 15) == 0;
 #pragma unroll
-  for (int g = 0; g < NG; ++g) *reinterpret_cast<uint4*>(p.out + (size_t)m[g] * p.out_ld + co[g]) = pack8(y + 8 * g);
+  for (int g = 0; g < NG; g += 2) {  // groups g, g + 1 are 16 consecutive channels of one output pixel unless a class ends between them
+    act_t* const o0 = p.out + (size_t)m[g] * p.out_ld + co[g];
+    if (g + 1 < NG && wide_st && m[g + 1] == m[g] && co[g + 1] == co[g] + 8 && (co[g] & 15) == 0) {
+      st_global_256(o0, pack8(y + 8 * g), pack8(y + 8 * g + 8));
+    } else {
+      *reinterpret_cast<uint4*>(o0) = pack8(y + 8 * g);
+      if (g + 1 < NG) *reinterpret_cast<uint4*>(p.out + (size_t)m[g + 1] * p.out_ld + co[g + 1]) = pack8(y + 8 * g + 8);
+    }
+  }
 }
 
 template <int KIND>
