@@ -76,7 +76,12 @@ __device__ __forceinline__ void load_ln_tile(const LinAttnFusedParams& p, int ro
     if (ok) {
       const uint4* src = reinterpret_cast<const uint4*>(p.x + ((size_t)row * p.n + pix) * C + part * 32);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) unpack8(__ldg(src + i), v + 8 * i);
+      for (int i = 0; i < 4; i += 2) {  // 64 contiguous bytes per thread: two 256-bit loads
+        uint4 a, b;
+        ld_global_nc_256(src + i, a, b);
+        unpack8(a, v + 8 * i);
+        unpack8(b, v + 8 * i + 8);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = 0.f;

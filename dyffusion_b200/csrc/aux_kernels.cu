@@ -190,16 +190,21 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const Head1x1Params p) {
 #pragma unroll
   for (int o = 0; o < 8; ++o) acc[o] = o < p.OC ? s_w[p.OC * p.C + o] : 0.f;
   const uint4* xp = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.C);
-  for (int c8 = 0; c8 < p.C / 8; ++c8) {
-    float f[8];
-    unpack8(__ldg(xp + c8), f);
+  for (int c8 = 0; c8 < p.C / 8; c8 += 2) {  // (C % 16 == 0, checked by the launcher: 256-bit loads)
+    uint4 u0, u1;
+    ld_global_nc_256(xp + c8, u0, u1);
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
-      if (o < p.OC) {
-        const float* w = s_w + o * p.C + c8 * 8;
+    for (int h = 0; h < 2; ++h) {
+      float f[8];
+      unpack8(h ? u1 : u0, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], w[j], acc[o]);
-      }
+      for (int o = 0; o < 8; ++o)
+        if (o < p.OC) {
+          const float* w = s_w + o * p.C + (c8 + h) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], w[j], acc[o]);
+        }
+    }
   }
   const long long r = m / p.HW, pix = m - r * p.HW;
   for (int o = 0; o < p.OC; ++o) p.y[((size_t)r * p.OC + o) * p.HW + pix] = acc[o];
@@ -962,7 +967,7 @@ __global__ void dropout_mask_kernel(DropCfg d, long long n, uint8_t* mask) {
 }  // namespace
 
 int launch_head1x1(const Head1x1Params& p, cudaStream_t s) {
-  if (p.OC > 8 || p.C % 8) { set_error("head1x1: needs <= 8 output channels and C % 8 == 0"); return -1; }
+  if (p.OC > 8 || p.C % 16) { set_error("head1x1: needs <= 8 output channels and C % 16 == 0"); return -1; }
   ProfScope prof(s, KC_ELEMENTWISE, 2.0 * (double)p.M * p.C * p.OC, (double)p.M * (2.0 * p.C + 4.0 * p.OC));
   head1x1_kernel<<<cdiv(p.M, 256), 256, (size_t)(p.OC * p.C + p.OC) * sizeof(float), s>>>(p);
   DYF_LAUNCH_OK("head1x1_kernel");

@@ -622,7 +622,7 @@ int Net::build_unet_resnet() {
     x = resnet_block("final_res_block", cat, 2 * dim, dim, site);
   }
   int fl = add_conv("final_conv", dim, d.out_channels, 1, 1, 0);
-  if (d.out_channels <= 8 && !getenv("DYF_DISABLE_HEAD1X1")) {  // a few output channels: one dot product per pixel, fp32 weights
+  if (d.out_channels <= 8 && dim % 16 == 0 && !getenv("DYF_DISABLE_HEAD1X1")) {  // a few output channels: one dot product per pixel, fp32 weights
     Op f{}; f.type = OP_HEAD1X1; f.in0 = x; f.layer = fl;
     ops.push_back(f);
   } else {
