@@ -18,6 +18,20 @@ class _FakeDiffusion:
         return {f"t{i}_preds": ic[:, -3:] * i + s for i in (1, 2, 3)}
 
 
+class _FakeEngineDiffusion(_FakeDiffusion):
+    """Like the engine drop-in, its `sample_loop` takes `row_offset` (index of the shard's first row in the un-sharded job, what
+    the dropout / noise streams are keyed by): the outputs record the GLOBAL row every local row believes it is."""
+
+    def sample_loop(self, initial_condition, static_condition=None, row_offset=0):
+        raise NotImplementedError
+
+    def sample(self, ic, static_condition=None, row_offset=0, **kw):
+        out = super().sample(ic, static_condition, **kw)
+        glob = torch.arange(ic.shape[0], dtype=ic.dtype).view(-1, 1, 1, 1) + float(row_offset)
+        out["t1_preds"] = out["t1_preds"] * 0 + glob
+        return out
+
+
 def _rollout_is_rank_invariant(rows):
     """The autoregressive rollout with its sampler calls sharded over the ranks returns, on every rank, what one process
     returns: member-major row order survives shard -> all-gather -> (N, B) un-stacking -> hand-off."""
@@ -54,6 +68,9 @@ def _worker(rank, world, port, rows, q):
         out = sample_sharded(_FakeDiffusion(), ic, st)
         ref = _FakeDiffusion().sample(ic, st)
         ok = sorted(out) == sorted(ref) and all(torch.equal(out[k], ref[k]) for k in ref)
+        # every rank hands its shard's first row to the sampler: gathered, the recorded global rows are 0 .. rows-1
+        rec = sample_sharded(_FakeEngineDiffusion(), ic, st)["t1_preds"]
+        ok = ok and torch.equal(rec[:, 0, 0, 0], torch.arange(rows, dtype=rec.dtype))
         # raw gather keeps rank order and drops the padding of a short tail shard
         b, e = shard_bounds(rows, world)[rank]
         local = torch.arange(b, e, dtype=torch.float32).view(1, -1, 1).repeat(2, 1, 3)
